@@ -1,0 +1,168 @@
+/*
+ * t2d_b200.h - C ABI of the B200-native batched env.step() hot path for tactics2d.
+ *
+ * The reference (WoodOxen/tactics2d, pure Python) has no FFI layer: its boundary for
+ * this path is five duck-typed Python interfaces.  This library is what a ctypes
+ * binding behind those interfaces calls; every entry point names the reference
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   t2d_physics_step     PhysicsModelBase.step            tactics2d/physics/physics_model_base.py:27-38
+ *                        SingleTrackKinematics.step       tactics2d/physics/single_track_kinematics.py:178-198
+ *                        SingleTrackDynamics.step         tactics2d/physics/single_track_dynamics.py:231-251
+ *                        PointMass.step                   tactics2d/physics/point_mass.py:209-232
+ *   t2d_set_type_table   ParticipantBase / templates      tactics2d/participant/element/participant_template.py:42-257,
+ *                                                         vehicle.py:111-118,179-221, cyclist.py:76-94, pedestrian.py:70-88
+ *   t2d_set_map          StaticCollision.reset / OutBound.reset
+ *                                                         tactics2d/traffic/event_detection/collision.py:45-46, out_bound.py:50-65
+ *   t2d_bind_state       Trajectory.add_state / current state
+ *                                                         tactics2d/participant/trajectory/trajectory.py:115-149
+ *   t2d_step             ScenarioManager.update + check_status
+ *                                                         tactics2d/traffic/scenario_manager.py:63-73,
+ *                                                         tactics2d/envs/parking.py:352-392 (tick), :243-248 (done rule)
+ *                        ParticipantBase.get_pose         tactics2d/participant/element/vehicle.py:263-281
+ *                        DynamicCollision.update          tactics2d/traffic/event_detection/collision.py:18-25
+ *                        StaticCollision.update           tactics2d/traffic/event_detection/collision.py:37-43
+ *                        OutBound.update                  tactics2d/traffic/event_detection/out_bound.py:37-48
+ *                        TimeExceed.update                tactics2d/traffic/event_detection/time_exceed.py:26-33
+ *   t2d_check_events     the same detectors on caller-supplied poses (no physics)
+ *   t2d_reset            ScenarioManager.reset / ParticipantBase.reset
+ *                                                         tactics2d/envs/parking.py:397-441, participant_base.py:236-246
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the ABI;
+ *   - every function returns 0 on success or a negative T2D_E_* code; the message of the
+ *     last error on the calling thread is t2d_last_error(); no exception crosses;
+ *   - all array arguments of t2d_step / t2d_check_events / t2d_reset / t2d_physics_step are
+ *     DEVICE pointers owned by the caller (PyTorch tensors' data_ptr()); the library never
+ *     allocates or frees them.  t2d_set_type_table / t2d_set_map take HOST pointers and copy;
+ *   - work is enqueued on the cudaStream_t passed as `stream` (NULL = legacy default
+ *     stream) and the call returns without a host synchronisation;
+ *   - a context belongs to one device and is not thread-safe.
+ *
+ * Layout: structure-of-arrays, scenario-major.  Participant (n, m) of an N x M world lives
+ * at index n*M + m of every [N, M] array.  fp32 state, uint8 type ids, int16 hit indices.
+ */
+#ifndef T2D_B200_H
+#define T2D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2D_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define T2D_OK 0
+#define T2D_E_INVALID (-1)     /* bad argument */
+#define T2D_E_CUDA (-2)        /* a CUDA runtime call failed; see t2d_last_error() */
+#define T2D_E_UNSUPPORTED (-3) /* configuration outside what the kernels cover */
+#define T2D_E_STATE (-4)       /* call order: state not bound, type table not set ... */
+
+/* physics model ids (t2d_type_params.model) */
+#define T2D_MODEL_KINEMATICS 0       /* SingleTrackKinematics  */
+#define T2D_MODEL_DYNAMICS 1         /* SingleTrackDynamics    */
+#define T2D_MODEL_POINTMASS_NEWTON 2 /* PointMass(backend="newton") */
+#define T2D_MODEL_POINTMASS_EULER 3  /* PointMass(backend="euler")  */
+#define T2D_MODEL_STATIC 4           /* no motion (Obstacle, obstacle.py:14-19) */
+
+/* collision shape ids (t2d_type_params.shape) */
+#define T2D_SHAPE_OBB 0    /* Vehicle / Cyclist / Other bounding box, vehicle.py:132-142 */
+#define T2D_SHAPE_CIRCLE 1 /* Pedestrian ((x, y), width/2), pedestrian.py:85-88 */
+#define T2D_SHAPE_NONE 2   /* takes part in physics only */
+
+#define T2D_TYPE_INACTIVE 255 /* type id of an empty participant slot */
+#define T2D_MAX_TYPES 64
+#define T2D_MAX_PARTICIPANTS 128 /* per scenario (one warp spans a scenario) */
+#define T2D_MAX_SEGMENTS 32767   /* hit_segment is int16 */
+
+/* per-participant event byte (t2d_step `flags`) */
+#define T2D_F_DYNAMIC 1  /* TrafficStatus.COLLISION_DYNAMIC, status.py:55 */
+#define T2D_F_STATIC 2   /* TrafficStatus.COLLISION_STATIC,  status.py:54 */
+#define T2D_F_OUTBOUND 4 /* ScenarioStatus.OUT_BOUND,        status.py:26 */
+
+/* scenario status byte = ScenarioStatus, tactics2d/traffic/status.py:23-28 */
+#define T2D_STATUS_NORMAL 1
+#define T2D_STATUS_COMPLETED 2
+#define T2D_STATUS_TIME_EXCEEDED 3
+#define T2D_STATUS_OUT_BOUND 4
+#define T2D_STATUS_NO_ACTION 5
+#define T2D_STATUS_FAILED 6
+
+/* t2d_config.flags */
+#define T2D_CFG_ANY_PARTICIPANT 1 /* any active participant's event ends the scenario (default: only participant 0, the ego) */
+#define T2D_CFG_STEER_FIRST 2     /* action[...,0] is steering, [...,1] acceleration (env order, parking.py:239) */
+
+typedef struct t2d_ctx t2d_ctx;
+
+typedef struct t2d_config {
+  int32_t interval_ms; /* State.frame advance per step; ScenarioManager.step_size (scenario_manager.py:50) */
+  int32_t delta_t_ms;  /* Euler sub-step; PhysicsModelBase._DELTA_T = 5 (physics_model_base.py:23) */
+  int32_t max_step;    /* TimeExceed.max_step; <= 0 disables the check */
+  int32_t flags;       /* T2D_CFG_* */
+} t2d_config;
+
+/* One row per participant type.  Ranges are [lo, hi]; "no constraint" (the reference's
+ * None) is (-INFINITY, +INFINITY). */
+typedef struct t2d_type_params {
+  float half_len, half_wid; /* OBB half extents (length/2, width/2) */
+  float radius;             /* circle radius (width/2) */
+  float lf, lr;             /* axle distances from the geometry centre */
+  float steer_lo, steer_hi;
+  float speed_lo, speed_hi;
+  float accel_lo, accel_hi;
+  float mass, mass_height, mu, I_z, cf, cr; /* SingleTrackDynamics only */
+  int32_t model;                            /* T2D_MODEL_* */
+  int32_t shape;                            /* T2D_SHAPE_* */
+} t2d_type_params;
+
+int t2d_version(void);
+const char* t2d_last_error(void);
+
+int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, const t2d_config* cfg);
+int t2d_destroy(t2d_ctx* ctx);
+int t2d_set_config(t2d_ctx* ctx, const t2d_config* cfg);
+
+/* HOST pointers; copied. */
+int t2d_set_type_table(t2d_ctx* ctx, const t2d_type_params* table, int n_types);
+/* segments: host float[n_seg][4] = (x1, y1, x2, y2), collidable map polyline pieces in list
+ * order (the order defines "first hit"); bounds: host float[4] = (xmin, xmax, ymin, ymax) as
+ * Map.boundary gives it, or NULL for no out-of-bound check; cell_size: broadphase grid pitch
+ * in metres (<= 0: choose automatically). */
+int t2d_set_map(t2d_ctx* ctx, const float* segments, int n_seg, const float* bounds, float cell_size);
+
+/* DEVICE pointers, each [N, M] (step_count: [N]); read and written in place by t2d_step. */
+int t2d_bind_state(t2d_ctx* ctx, float* x, float* y, float* heading, float* speed, float* vx, float* vy,
+                   const uint8_t* type_id, int32_t* step_count);
+
+/* One tick of all N scenarios.  action: [N, M, 2] fp32.  Outputs (any may be NULL):
+ * flags [N, M] uint8, hit_index [N, M] int16 (lowest colliding participant or -1),
+ * hit_segment [N, M] int16 (lowest colliding map segment or -1), scn_status [N] uint8,
+ * done [N] uint8. */
+int t2d_step(t2d_ctx* ctx, const float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
+             uint8_t* scn_status, uint8_t* done, void* stream);
+
+/* The detectors alone on the bound poses (x, y, heading); no physics, no step counting. */
+int t2d_check_events(t2d_ctx* ctx, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, void* stream);
+
+/* Masked re-initialisation: for every scenario n with mask[n] != 0 copy row pool_index[n] of the
+ * [P, M] pool arrays into the bound state and zero step_count[n]. pool_type may be NULL. */
+int t2d_reset(t2d_ctx* ctx, const uint8_t* mask, const int32_t* pool_index, int n_pool, const float* pool_x,
+              const float* pool_y, const float* pool_heading, const float* pool_speed, const float* pool_vx,
+              const float* pool_vy, void* stream);
+
+/* Flat batch of `n` independent participants through ONE model (PhysicsModelBase.step):
+ * state arrays are read and written in place; action [n, 2]; applied [n, 2] (may be NULL)
+ * receives the clipped (accel, steer) the reference returns next to the State. */
+int t2d_physics_step(int device, const t2d_type_params* params /*host*/, int interval_ms, int delta_t_ms, int n,
+                     float* x, float* y, float* heading, float* speed, float* vx, float* vy, const float* action,
+                     float* applied, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t t2d_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2D_B200_H */

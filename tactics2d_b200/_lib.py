@@ -1,0 +1,75 @@
+"""ctypes binding of ``libt2d_b200.so`` (C ABI: ``include/t2d_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+CPU fallback: if the shared object is missing, loading fails loudly, and every compute entry
+point needs a CUDA device.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt2d_b200.so")
+
+
+class T2DError(RuntimeError):
+    """A C-ABI call returned a negative code; the message is ``t2d_last_error()``."""
+
+
+class Config(C.Structure):
+    _fields_ = [("interval_ms", C.c_int32), ("delta_t_ms", C.c_int32), ("max_step", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+class TypeParamsC(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "half_len", "half_wid", "radius", "lf", "lr", "steer_lo", "steer_hi", "speed_lo", "speed_hi",
+        "accel_lo", "accel_hi", "mass", "mass_height", "mu", "I_z", "cf", "cr")] + [
+        ("model", C.c_int32), ("shape", C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/t2d_b200.h declares
+_P = C.c_void_p
+SYMBOLS = {
+    "t2d_version": (C.c_int, []),
+    "t2d_last_error": (C.c_char_p, []),
+    "t2d_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.POINTER(Config)]),
+    "t2d_destroy": (C.c_int, [_P]),
+    "t2d_set_config": (C.c_int, [_P, C.POINTER(Config)]),
+    "t2d_set_type_table": (C.c_int, [_P, C.POINTER(TypeParamsC), C.c_int]),
+    "t2d_set_map": (C.c_int, [_P, _P, C.c_int, _P, C.c_float]),
+    "t2d_bind_state": (C.c_int, [_P] + [_P] * 8),
+    "t2d_step": (C.c_int, [_P] + [_P] * 7),
+    "t2d_check_events": (C.c_int, [_P] + [_P] * 4),
+    "t2d_reset": (C.c_int, [_P, _P, _P, C.c_int] + [_P] * 7),
+    "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 9),
+    "t2d_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a).  tactics2d_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int):
+    if code != 0:
+        msg = load().t2d_last_error()
+        raise T2DError(f"t2d error {code}: {msg.decode() if msg else ''}")

@@ -1,0 +1,841 @@
+// t2d_kernels.cu - sm_100a kernels and the C ABI (include/t2d_b200.h) of the batched tick.
+//
+// K1  t2d_step_kernel      fused physics -> pose -> dynamic collision (broadphase + filtered
+//                          narrowphase) -> static collision against the map tile in shared
+//                          memory (uniform-grid broadphase) -> out-of-bound -> status chain.
+// K2  t2d_reset_kernel     masked re-initialisation from a pool of initial states.
+// K3  t2d_physics_kernel   flat batch through one physics model (PhysicsModelBase.step).
+//
+// Work decomposition of K1: a scenario (M <= 128 participants) is owned by a group of G lanes of
+// one warp, 4 consecutive participants per lane (one float4 per state array per lane: coalesced
+// 128-bit loads, 4 independent Euler chains per thread for ILP).  G = pow2 >= ceil(M/4), so a
+// warp holds 32/G scenarios and every exchange inside a scenario is warp-synchronous: poses go
+// through a per-warp shared-memory tile + __syncwarp, reductions through shuffles.  CTAs are
+// persistent (grid = SMs x resident CTAs) and stage the static map tile (segments + broadphase
+// grid) into shared memory ONCE with a TMA bulk copy (cp.async.bulk + mbarrier) that overlaps
+// the first tile's physics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/t2d_b200.h"
+#include "t2d_math.cuh"
+
+namespace t2d {
+
+constexpr int PPL = 4;                  // participants per lane
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int POSE_PER_WARP = 128;      // 32 lanes x PPL
+constexpr int MAP_SMEM_LIMIT = 120 * 1024;
+
+struct MapHeader {   // 64 bytes, start of the map blob
+  int32_t n_seg, gx, gy, n_items;
+  float x0, y0, inv_cell, cell;
+  uint32_t off_seg, off_cell, off_items, total_bytes;
+  uint32_t pad[4];
+};
+static_assert(sizeof(MapHeader) == 64, "MapHeader must be 64 bytes");
+
+struct StepArgs {
+  float *x, *y, *h, *v, *vx, *vy;
+  const uint8_t* type_id;
+  int32_t* step_count;
+  const float* action;
+  uint8_t* flags;
+  int16_t* hit_index;
+  int16_t* hit_segment;
+  uint8_t* scn_status;
+  uint8_t* done;
+  const unsigned char* map_blob;   // device; nullptr when no segments
+  const Params* table;             // device
+  int map_bytes, map_in_smem;
+  int n_types;
+  int N, M, G;                     // G = lanes per scenario
+  int n_steps;
+  float dt, dt_rem;
+  double dt_d, dt_rem_d, interval_d;   // the same steps in double (dynamics / point mass run in fp64)
+  int max_step, cfg_flags;
+  int do_physics, has_bounds, vec_ok, needs_vel_in;
+  float bxmin, bxmax, bymin, bymax;
+};
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- pair narrowphase
+// A pose is (x, y, heading, c, s, l, w); w < 0 marks a disc of radius l.
+struct Pose {
+  float x, y, h, c, s, l, w;
+};
+
+__device__ __noinline__ bool pair_exact(const Pose a, const Pose b) {
+  const bool ca = a.w < 0.0f, cb = b.w < 0.0f;
+  if (!ca && !cb) return obb_obb_f64(a.x, a.y, a.h, a.l, a.w, b.x, b.y, b.h, b.l, b.w);
+  if (!ca && cb) return obb_circle_f64(a.x, a.y, a.h, a.l, a.w, b.x, b.y, b.l);
+  if (ca && !cb) return obb_circle_f64(b.x, b.y, b.h, b.l, b.w, a.x, a.y, a.l);
+  return circle_circle_f64(a.x, a.y, a.l, b.x, b.y, b.l);
+}
+
+__device__ __forceinline__ bool pair_hit(const Pose& a, const Pose& b) {
+  const bool ca = a.w < 0.0f, cb = b.w < 0.0f;
+  int r;
+  if (!ca && !cb) r = obb_obb_f32(a.x, a.y, a.c, a.s, a.l, a.w, b.x, b.y, b.c, b.s, b.l, b.w);
+  else if (!ca && cb) r = obb_circle_f32(a.x, a.y, a.c, a.s, a.l, a.w, b.x, b.y, b.l);
+  else if (ca && !cb) r = obb_circle_f32(b.x, b.y, b.c, b.s, b.l, b.w, a.x, a.y, a.l);
+  else r = circle_circle_f32(a.x, a.y, a.l, b.x, b.y, b.l);
+  if (r < 0) return pair_exact(a, b);
+  return r != 0;
+}
+
+__device__ __noinline__ bool seg_exact(const Pose a, const float4 sg) {
+  if (a.w < 0.0f) return circle_segment_f64(a.x, a.y, a.l, sg.x, sg.y, sg.z, sg.w);
+  return obb_segment_f64(a.x, a.y, a.h, a.l, a.w, sg.x, sg.y, sg.z, sg.w);
+}
+
+__device__ __forceinline__ bool seg_hit(const Pose& a, const float4 sg) {
+  int r = a.w < 0.0f ? circle_segment_f32(a.x, a.y, a.l, sg.x, sg.y, sg.z, sg.w)
+                     : obb_segment_f32(a.x, a.y, a.c, a.s, a.l, a.w, sg.x, sg.y, sg.z, sg.w);
+  if (r < 0) return seg_exact(a, sg);
+  return r != 0;
+}
+
+__device__ __noinline__ bool oob_exact(const Pose a, float xmin, float xmax, float ymin, float ymax) {
+  return out_of_bound_f64(a.x, a.y, a.h, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax);
+}
+
+// Every model except the fp32 kinematic fast path (one copy of the fp64 code per kernel).
+__device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem, double interval) {
+  if (p.model == MODEL_DYNAMICS) {
+    dynamics_step(io, p, n_steps, dt);
+  } else if (p.model == MODEL_POINTMASS_NEWTON) {
+    pointmass_newton_step(io, p, interval);
+  } else if (p.model == MODEL_POINTMASS_EULER) {
+    pointmass_euler_step(io, p, n_steps, dt, dt_rem);
+  } else {
+    sincosf(io.h, &io.sh, &io.ch);
+  }
+}
+
+// First (lowest-index) map segment the pose touches, or -1.  Uniform-grid broadphase over the map
+// tile: only the cells under the pose's bounding circle are visited.
+__device__ __noinline__ int static_first_hit(const Pose a, const float rbound, const unsigned char* mapb) {
+  const MapHeader* mh = reinterpret_cast<const MapHeader*>(mapb);
+  const float4* seg = reinterpret_cast<const float4*>(mapb + mh->off_seg);
+  const uint32_t* cell_start = reinterpret_cast<const uint32_t*>(mapb + mh->off_cell);
+  const uint16_t* items = reinterpret_cast<const uint16_t*>(mapb + mh->off_items);
+  const int gx = mh->gx, gy = mh->gy;
+  const float x0 = mh->x0, y0 = mh->y0, inv = mh->inv_cell;
+  const float r = rbound * 1.0001f + 1e-3f;
+  int cx0 = (int)floorf((a.x - r - x0) * inv), cx1 = (int)floorf((a.x + r - x0) * inv);
+  int cy0 = (int)floorf((a.y - r - y0) * inv), cy1 = (int)floorf((a.y + r - y0) * inv);
+  cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, gx - 1); cy1 = min(cy1, gy - 1);
+  int best = 0x7fffffff;
+  for (int cy = cy0; cy <= cy1; ++cy) {
+    for (int cx = cx0; cx <= cx1; ++cx) {
+      const int cidx = cy * gx + cx;
+      const uint32_t b = cell_start[cidx], e = cell_start[cidx + 1];
+      for (uint32_t k = b; k < e; ++k) {
+        const int sidx = items[k];
+        if (sidx >= best) break;   // lists are ascending: nothing better left in this cell
+        if (seg_hit(a, seg[sidx])) best = sidx;
+      }
+    }
+  }
+  return best == 0x7fffffff ? -1 : best;
+}
+
+// ---------------------------------------------------------------------------- K1
+__global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_constant__ StepArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // carve: [map blob | 16B aligned] [type table] [pose tiles] [mbarrier]
+  const int map_smem_bytes = A.map_in_smem ? A.map_bytes : 0;
+  unsigned char* s_map = smem;
+  Params* s_table = reinterpret_cast<Params*>(smem + map_smem_bytes);
+  const int table_bytes = ((A.n_types * (int)sizeof(Params) + 15) / 16) * 16;
+  float4* s_poseA = reinterpret_cast<float4*>(smem + map_smem_bytes + table_bytes);
+  float4* s_poseB = s_poseA + WARPS_PER_CTA * POSE_PER_WARP;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_poseB + WARPS_PER_CTA * POSE_PER_WARP);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0 && map_smem_bytes > 0) {
+    mbar_init(s_bar, 1);
+    fence_mbar_init();
+  }
+  {
+    const int words = A.n_types * (int)(sizeof(Params) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.table);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_table);
+    for (int i = tid; i < words; i += CTA_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (tid == 0 && map_smem_bytes > 0) {
+    mbar_expect_tx(s_bar, (uint32_t)map_smem_bytes);
+    bulk_g2s(s_map, A.map_blob, (uint32_t)map_smem_bytes, s_bar);
+  }
+  bool map_ready = (map_smem_bytes == 0);
+  const unsigned char* mapb = A.map_in_smem ? s_map : A.map_blob;
+
+  const int G = A.G, M = A.M;
+  const int spw = 32 / G;               // scenarios per warp
+  const int sub = lane / G;             // scenario slot inside the warp
+  const int gl = lane - sub * G;        // lane inside the group
+  const int m0 = gl * PPL;              // first participant of this lane
+  const int MP = G * PPL;               // padded participants per scenario
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+  float4* poseA = s_poseA + warp * POSE_PER_WARP + sub * MP;
+  float4* poseB = s_poseB + warp * POSE_PER_WARP + sub * MP;
+
+  const long long n_tiles = ((long long)A.N + spw - 1) / spw;
+  for (long long tile = (long long)blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles;
+       tile += (long long)gridDim.x * WARPS_PER_CTA) {
+    const long long n = tile * spw + sub;
+    const bool scn_ok = n < A.N;
+    int nvalid = scn_ok ? min(PPL, M - m0) : 0;
+    if (nvalid < 0) nvalid = 0;
+    const long long idx0 = n * M + m0;
+
+    // ------------------------------------------------------------------ load
+    float sx[PPL], sy[PPL], shd[PPL], sv[PPL], svx[PPL], svy[PPL], a0[PPL], a1[PPL];
+    int tidv[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      sx[i] = sy[i] = shd[i] = sv[i] = svx[i] = svy[i] = a0[i] = a1[i] = 0.0f;
+      tidv[i] = T2D_TYPE_INACTIVE;
+    }
+    if (nvalid == PPL && A.vec_ok) {
+      const float4 X = *reinterpret_cast<const float4*>(A.x + idx0);
+      const float4 Y = *reinterpret_cast<const float4*>(A.y + idx0);
+      const float4 H = *reinterpret_cast<const float4*>(A.h + idx0);
+      const float4 V = *reinterpret_cast<const float4*>(A.v + idx0);
+      const uchar4 T = *reinterpret_cast<const uchar4*>(A.type_id + idx0);
+      sx[0] = X.x; sx[1] = X.y; sx[2] = X.z; sx[3] = X.w;
+      sy[0] = Y.x; sy[1] = Y.y; sy[2] = Y.z; sy[3] = Y.w;
+      shd[0] = H.x; shd[1] = H.y; shd[2] = H.z; shd[3] = H.w;
+      sv[0] = V.x; sv[1] = V.y; sv[2] = V.z; sv[3] = V.w;
+      tidv[0] = T.x; tidv[1] = T.y; tidv[2] = T.z; tidv[3] = T.w;
+      if (A.do_physics) {
+        const float4 P0 = *reinterpret_cast<const float4*>(A.action + 2 * idx0);
+        const float4 P1 = *reinterpret_cast<const float4*>(A.action + 2 * idx0 + 4);
+        a0[0] = P0.x; a1[0] = P0.y; a0[1] = P0.z; a1[1] = P0.w;
+        a0[2] = P1.x; a1[2] = P1.y; a0[3] = P1.z; a1[3] = P1.w;
+        if (A.needs_vel_in) {
+          const float4 VX = *reinterpret_cast<const float4*>(A.vx + idx0);
+          const float4 VY = *reinterpret_cast<const float4*>(A.vy + idx0);
+          svx[0] = VX.x; svx[1] = VX.y; svx[2] = VX.z; svx[3] = VX.w;
+          svy[0] = VY.x; svy[1] = VY.y; svy[2] = VY.z; svy[3] = VY.w;
+        }
+      }
+    } else {
+      for (int i = 0; i < nvalid; ++i) {
+        sx[i] = A.x[idx0 + i]; sy[i] = A.y[idx0 + i]; shd[i] = A.h[idx0 + i]; sv[i] = A.v[idx0 + i];
+        tidv[i] = A.type_id[idx0 + i];
+        if (A.do_physics) {
+          a0[i] = A.action[2 * (idx0 + i)]; a1[i] = A.action[2 * (idx0 + i) + 1];
+          if (A.needs_vel_in) { svx[i] = A.vx[idx0 + i]; svy[i] = A.vy[idx0 + i]; }
+        }
+      }
+    }
+    if (A.cfg_flags & T2D_CFG_STEER_FIRST) {
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const Params& p = s_table[tidv[i] < A.n_types ? tidv[i] : 0];
+        if (p.model <= MODEL_DYNAMICS) { float t = a0[i]; a0[i] = a1[i]; a1[i] = t; }
+      }
+    }
+
+    // ------------------------------------------------------------------ physics
+    float ch[PPL], sh[PPL];
+    bool active[PPL];
+    const Params* pp[PPL];
+    bool all_kin = true;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      active[i] = tidv[i] < A.n_types;
+      pp[i] = &s_table[active[i] ? tidv[i] : 0];
+      all_kin = all_kin && active[i] && (pp[i]->model == MODEL_KINEMATICS);
+    }
+    if (A.do_physics) {
+      if (__all_sync(0xffffffffu, all_kin)) {
+        KinIO<PPL> io;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          io.x[i] = sx[i]; io.y[i] = sy[i]; io.h[i] = shd[i]; io.v[i] = sv[i];
+          io.acc[i] = a0[i]; io.steer[i] = a1[i];
+        }
+        kinematics_step<PPL>(io, pp, A.n_steps, A.dt, A.dt_rem);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          sx[i] = io.x[i]; sy[i] = io.y[i]; shd[i] = io.h[i]; sv[i] = io.v[i];
+          svx[i] = io.vx[i]; svy[i] = io.vy[i]; ch[i] = io.ch[i]; sh[i] = io.sh[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          if (!active[i]) {
+            ch[i] = 1.0f; sh[i] = 0.0f;
+          } else if (pp[i]->model == MODEL_KINEMATICS) {
+            KinIO<1> io;
+            io.x[0] = sx[i]; io.y[0] = sy[i]; io.h[0] = shd[i]; io.v[0] = sv[i];
+            io.acc[0] = a0[i]; io.steer[0] = a1[i];
+            const Params* const p1[1] = {pp[i]};
+            kinematics_step<1>(io, p1, A.n_steps, A.dt, A.dt_rem);
+            sx[i] = io.x[0]; sy[i] = io.y[0]; shd[i] = io.h[0]; sv[i] = io.v[0];
+            svx[i] = io.vx[0]; svy[i] = io.vy[0]; ch[i] = io.ch[0]; sh[i] = io.sh[0];
+          } else {
+            OneIO io;
+            io.x = sx[i]; io.y = sy[i]; io.h = shd[i]; io.v = sv[i]; io.vx = svx[i]; io.vy = svy[i];
+            io.a0 = a0[i]; io.a1 = a1[i];
+            io.ch = 1.0f; io.sh = 0.0f;
+            other_model_step(io, *pp[i], A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
+            sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
+            ch[i] = io.ch; sh[i] = io.sh;
+          }
+        }
+      }
+      // ---------------------------------------------------------------- store state
+      if (nvalid == PPL && A.vec_ok) {
+        *reinterpret_cast<float4*>(A.x + idx0) = make_float4(sx[0], sx[1], sx[2], sx[3]);
+        *reinterpret_cast<float4*>(A.y + idx0) = make_float4(sy[0], sy[1], sy[2], sy[3]);
+        *reinterpret_cast<float4*>(A.h + idx0) = make_float4(shd[0], shd[1], shd[2], shd[3]);
+        *reinterpret_cast<float4*>(A.v + idx0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+        *reinterpret_cast<float4*>(A.vx + idx0) = make_float4(svx[0], svx[1], svx[2], svx[3]);
+        *reinterpret_cast<float4*>(A.vy + idx0) = make_float4(svy[0], svy[1], svy[2], svy[3]);
+      } else {
+        for (int i = 0; i < nvalid; ++i) {
+          if (!active[i]) continue;
+          A.x[idx0 + i] = sx[i]; A.y[idx0 + i] = sy[i]; A.h[idx0 + i] = shd[i]; A.v[idx0 + i] = sv[i];
+          A.vx[idx0 + i] = svx[i]; A.vy[idx0 + i] = svy[i];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) sincosf(shd[i], &sh[i], &ch[i]);
+    }
+
+    // ------------------------------------------------------------------ poses -> shared
+    Pose my[PPL];
+    float rb[PPL];
+    bool solid[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const Params& p = *pp[i];
+      solid[i] = active[i] && p.shape != SHAPE_NONE;
+      const bool circle = p.shape == SHAPE_CIRCLE;
+      my[i].x = sx[i]; my[i].y = sy[i]; my[i].h = shd[i]; my[i].c = ch[i]; my[i].s = sh[i];
+      my[i].l = circle ? p.radius : p.half_len;
+      my[i].w = circle ? -1.0f : p.half_wid;
+      // bounding radius, rounded up so the broadphase is conservative
+      rb[i] = circle ? p.radius : sqrtf(fmaf(p.half_len, p.half_len, p.half_wid * p.half_wid)) * 1.000001f;
+      poseA[m0 + i] = make_float4(solid[i] ? sx[i] : __int_as_float(0x7fc00000), sy[i], rb[i], shd[i]);
+      poseB[m0 + i] = make_float4(ch[i], sh[i], my[i].l, my[i].w);
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ dynamic collision
+    int hit[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) hit[i] = -1;
+    for (int j = 0; j < M; ++j) {
+      const float4 pa = poseA[j];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const float dx = pa.x - my[i].x, dy = pa.y - my[i].y;
+        const float rr = rb[i] + pa.z;
+        // NaN x (non-solid partner) fails the comparison; the margin keeps the filter conservative
+        const bool cand = fmaf(dx, dx, dy * dy) <= rr * rr * 1.00001f + 1e-12f;
+        if (cand && solid[i] && hit[i] < 0 && j != m0 + i) {
+          const float4 pb = poseB[j];
+          Pose o;
+          o.x = pa.x; o.y = pa.y; o.h = pa.w; o.c = pb.x; o.s = pb.y; o.l = pb.z; o.w = pb.w;
+          if (pair_hit(my[i], o)) hit[i] = j;
+        }
+      }
+    }
+
+    // ------------------------------------------------------------------ static collision
+    int hseg[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) hseg[i] = -1;
+    if (mapb != nullptr) {
+      if (!map_ready) {
+        mbar_wait(s_bar, 0);
+        map_ready = true;
+      }
+#pragma unroll
+      for (int i = 0; i < PPL; ++i)
+        if (solid[i]) hseg[i] = static_first_hit(my[i], rb[i], mapb);
+    }
+
+    // ------------------------------------------------------------------ out of bound + flags
+    uint8_t fl[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      uint8_t f = 0;
+      if (hit[i] >= 0) f |= T2D_F_DYNAMIC;
+      if (hseg[i] >= 0) f |= T2D_F_STATIC;
+      if (A.has_bounds && solid[i]) {
+        int r = out_of_bound_f32(my[i].x, my[i].y, my[i].c, my[i].s, my[i].l, my[i].w, my[i].w < 0.0f, A.bxmin, A.bxmax,
+                                 A.bymin, A.bymax);
+        if (r < 0) r = oob_exact(my[i], A.bxmin, A.bxmax, A.bymin, A.bymax) ? 1 : 0;
+        if (r) f |= T2D_F_OUTBOUND;
+      }
+      fl[i] = f;
+    }
+    if (nvalid == PPL && A.vec_ok) {
+      if (A.flags) *reinterpret_cast<uchar4*>(A.flags + idx0) = make_uchar4(fl[0], fl[1], fl[2], fl[3]);
+      if (A.hit_index)
+        *reinterpret_cast<short4*>(A.hit_index + idx0) = make_short4((short)hit[0], (short)hit[1], (short)hit[2], (short)hit[3]);
+      if (A.hit_segment)
+        *reinterpret_cast<short4*>(A.hit_segment + idx0) =
+            make_short4((short)hseg[0], (short)hseg[1], (short)hseg[2], (short)hseg[3]);
+    } else {
+      for (int i = 0; i < nvalid; ++i) {
+        if (A.flags) A.flags[idx0 + i] = fl[i];
+        if (A.hit_index) A.hit_index[idx0 + i] = (int16_t)hit[i];
+        if (A.hit_segment) A.hit_segment[idx0 + i] = (int16_t)hseg[i];
+      }
+    }
+
+    // ------------------------------------------------------------------ scenario status
+    if (A.do_physics) {
+      unsigned agg;
+      if (A.cfg_flags & T2D_CFG_ANY_PARTICIPANT) {
+        agg = fl[0] | fl[1] | fl[2] | fl[3];
+        for (int o = G >> 1; o > 0; o >>= 1) agg |= __shfl_xor_sync(0xffffffffu, agg, o);
+      } else {
+        agg = __shfl_sync(0xffffffffu, (unsigned)fl[0], sub * G);   // participant 0 = the ego
+      }
+      if (gl == 0 && scn_ok) {
+        const int cnt = A.step_count[n] + 1;                         // parking.py:353
+        A.step_count[n] = cnt;
+        uint8_t st = T2D_STATUS_NORMAL;
+        if (agg & T2D_F_DYNAMIC) st = T2D_STATUS_FAILED;
+        if (agg & T2D_F_STATIC) st = T2D_STATUS_FAILED;              // parking.py:381-385
+        if (agg & T2D_F_OUTBOUND) st = T2D_STATUS_OUT_BOUND;         // parking.py:376-379
+        if (A.max_step > 0 && cnt > A.max_step) st = T2D_STATUS_TIME_EXCEEDED;  // parking.py:366-369
+        if (A.scn_status) A.scn_status[n] = st;
+        if (A.done) A.done[n] = st != T2D_STATUS_NORMAL;             // parking.py:243-248
+      }
+    }
+    __syncwarp();   // pose tile is reused by the next tile
+  }
+  if (!map_ready) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
+}
+
+// ---------------------------------------------------------------------------- K2
+struct ResetArgs {
+  float *x, *y, *h, *v, *vx, *vy;
+  int32_t* step_count;
+  const uint8_t* mask;
+  const int32_t* pool_index;
+  const float *px, *py, *ph, *pv, *pvx, *pvy;
+  int N, M, n_pool;
+};
+
+__global__ void t2d_reset_kernel(const __grid_constant__ ResetArgs A) {
+  const long long total = (long long)A.N * A.M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / A.M), m = (int)(i - (long long)n * A.M);
+    if (!A.mask[n]) continue;
+    int r = A.pool_index ? A.pool_index[n] : n;
+    r = min(max(r, 0), A.n_pool - 1);
+    const long long s = (long long)r * A.M + m;
+    A.x[i] = A.px[s]; A.y[i] = A.py[s]; A.h[i] = A.ph[s]; A.v[i] = A.pv[s];
+    A.vx[i] = A.pvx ? A.pvx[s] : A.pv[s] * cosf(A.ph[s]);
+    A.vy[i] = A.pvy ? A.pvy[s] : A.pv[s] * sinf(A.ph[s]);
+    if (m == 0) A.step_count[n] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------- K3
+struct PhysArgs {
+  Params p;
+  float *x, *y, *h, *v, *vx, *vy;
+  const float* action;
+  float* applied;
+  int n, n_steps;
+  float dt, dt_rem;
+  double dt_d, dt_rem_d, interval_d;
+};
+
+__global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant__ PhysArgs A) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (long long)gridDim.x * blockDim.x) {
+    if (A.p.model == MODEL_KINEMATICS) {
+      KinIO<1> io;
+      io.x[0] = A.x[i]; io.y[0] = A.y[i]; io.h[0] = A.h[i]; io.v[0] = A.v[i];
+      io.acc[0] = A.action[2 * i]; io.steer[0] = A.action[2 * i + 1];
+      const Params* const p1[1] = {&A.p};
+      kinematics_step<1>(io, p1, A.n_steps, A.dt, A.dt_rem);
+      A.x[i] = io.x[0]; A.y[i] = io.y[0]; A.h[i] = io.h[0]; A.v[i] = io.v[0]; A.vx[i] = io.vx[0]; A.vy[i] = io.vy[0];
+      if (A.applied) { A.applied[2 * i] = io.acc[0]; A.applied[2 * i + 1] = io.steer[0]; }
+    } else {
+      OneIO io;
+      io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = A.vx[i]; io.vy = A.vy[i];
+      io.a0 = A.action[2 * i]; io.a1 = A.action[2 * i + 1];
+      io.ch = 1.0f; io.sh = 0.0f;
+      other_model_step(io, A.p, A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
+      A.x[i] = io.x; A.y[i] = io.y; A.h[i] = io.h; A.v[i] = io.v; A.vx[i] = io.vx; A.vy[i] = io.vy;
+      if (A.applied) { A.applied[2 * i] = io.a0; A.applied[2 * i + 1] = io.a1; }
+    }
+  }
+}
+
+}  // namespace t2d
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace t2d;
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(T2D_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct t2d_ctx {
+  int device = 0, N = 0, M = 0, G = 0;
+  t2d_config cfg{};
+  int n_types = 0;
+  bool has_pointmass = false;
+  Params* d_table = nullptr;
+  unsigned char* d_map = nullptr;
+  int map_bytes = 0;
+  bool has_bounds = false;
+  float bounds[4] = {0, 0, 0, 0};
+  float *x = nullptr, *y = nullptr, *h = nullptr, *v = nullptr, *vx = nullptr, *vy = nullptr;
+  const uint8_t* type_id = nullptr;
+  int32_t* step_count = nullptr;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  int configured_smem = -1;
+};
+
+extern "C" {
+
+int t2d_version(void) { return T2D_VERSION; }
+const char* t2d_last_error(void) { return g_err.c_str(); }
+int64_t t2d_launch_count(void) { return (int64_t)g_launches.load(); }
+
+static int check_cfg(const t2d_config* cfg) {
+  if (!cfg) return fail(T2D_E_INVALID, "cfg is NULL");
+  if (cfg->interval_ms <= 0) return fail(T2D_E_INVALID, "interval_ms must be > 0");
+  if (cfg->delta_t_ms <= 0) return fail(T2D_E_INVALID, "delta_t_ms must be > 0");
+  return T2D_OK;
+}
+
+int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, const t2d_config* cfg) {
+  if (!out) return fail(T2D_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int r = check_cfg(cfg)) return r;
+  if (n_scenarios <= 0 || m_participants <= 0) return fail(T2D_E_INVALID, "n_scenarios and m_participants must be > 0");
+  if (m_participants > T2D_MAX_PARTICIPANTS)
+    return fail(T2D_E_UNSUPPORTED, "m_participants > 128: a scenario must fit one warp (4 participants per lane)");
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(T2D_E_INVALID, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  t2d_ctx* c = new t2d_ctx();
+  c->device = device;
+  c->N = n_scenarios;
+  c->M = m_participants;
+  int g = 1;
+  while (g * PPL < m_participants) g <<= 1;
+  c->G = g;
+  c->cfg = *cfg;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = c;
+  return T2D_OK;
+}
+
+int t2d_destroy(t2d_ctx* c) {
+  if (!c) return T2D_OK;
+  cudaSetDevice(c->device);
+  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_map) cudaFree(c->d_map);
+  delete c;
+  return T2D_OK;
+}
+
+int t2d_set_config(t2d_ctx* c, const t2d_config* cfg) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (int r = check_cfg(cfg)) return r;
+  c->cfg = *cfg;
+  return T2D_OK;
+}
+
+int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
+  if (!c || !table) return fail(T2D_E_INVALID, "ctx/table is NULL");
+  if (n_types <= 0 || n_types > T2D_MAX_TYPES) return fail(T2D_E_INVALID, "n_types must be in 1..64");
+  static_assert(sizeof(t2d_type_params) == sizeof(Params), "type table layout");
+  c->has_pointmass = false;
+  for (int i = 0; i < n_types; ++i) {
+    const t2d_type_params& p = table[i];
+    if (p.model < 0 || p.model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "type table: unknown model id");
+    if (p.shape < 0 || p.shape > T2D_SHAPE_NONE) return fail(T2D_E_INVALID, "type table: unknown shape id");
+    if (p.model <= T2D_MODEL_DYNAMICS && !(p.lf + p.lr > 0.0f)) return fail(T2D_E_INVALID, "type table: lf + lr must be > 0");
+    if (p.model == T2D_MODEL_DYNAMICS && !(p.lf > 0.0f && p.I_z > 0.0f))
+      return fail(T2D_E_INVALID, "type table: dynamics needs lf > 0 and I_z > 0");
+    if (p.shape == T2D_SHAPE_OBB && !(p.half_len >= 0.0f && p.half_wid >= 0.0f))
+      return fail(T2D_E_INVALID, "type table: negative OBB half extent");
+    if (p.shape == T2D_SHAPE_CIRCLE && !(p.radius >= 0.0f)) return fail(T2D_E_INVALID, "type table: negative radius");
+    if (p.model == T2D_MODEL_POINTMASS_NEWTON || p.model == T2D_MODEL_POINTMASS_EULER) c->has_pointmass = true;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->d_table) CUDA_TRY(cudaMalloc(&c->d_table, T2D_MAX_TYPES * sizeof(Params)));
+  CUDA_TRY(cudaMemcpy(c->d_table, table, n_types * sizeof(Params), cudaMemcpyHostToDevice));
+  c->n_types = n_types;
+  return T2D_OK;
+}
+
+// Host-side build of the static broadphase: a uniform grid over the segments' bounding box; each
+// cell lists (ascending) the segments whose axis-aligned box, grown by a small margin, touches it.
+int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bounds, float cell_size) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (n_seg < 0 || n_seg > T2D_MAX_SEGMENTS) return fail(T2D_E_INVALID, "n_seg must be in 0..32767");
+  if (n_seg > 0 && !segments) return fail(T2D_E_INVALID, "segments is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->has_bounds = bounds != nullptr;
+  if (bounds) {
+    if (!(bounds[0] <= bounds[1] && bounds[2] <= bounds[3])) return fail(T2D_E_INVALID, "bounds must be (xmin<=xmax, ymin<=ymax)");
+    memcpy(c->bounds, bounds, sizeof(float) * 4);
+  }
+  if (c->d_map) {
+    cudaFree(c->d_map);
+    c->d_map = nullptr;
+  }
+  c->map_bytes = 0;
+  if (n_seg == 0) return T2D_OK;
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int i = 0; i < n_seg * 4; ++i)
+    if (!std::isfinite(segments[i])) return fail(T2D_E_INVALID, "segments must be finite");
+  for (int i = 0; i < n_seg; ++i) {
+    const float* s = segments + 4 * i;
+    xmin = std::min(xmin, std::min(s[0], s[2])); xmax = std::max(xmax, std::max(s[0], s[2]));
+    ymin = std::min(ymin, std::min(s[1], s[3])); ymax = std::max(ymax, std::max(s[1], s[3]));
+  }
+  const float span = std::max(xmax - xmin, ymax - ymin);
+  float cell = cell_size > 0.0f ? cell_size : 8.0f;
+  // keep the grid small enough for shared memory: at most 64 x 64 cells
+  while (span / cell > 64.0f) cell *= 2.0f;
+  const float margin = 1e-3f * std::max(1.0f, std::max(std::fabs(xmin) + std::fabs(xmax), std::fabs(ymin) + std::fabs(ymax)) * 1e-3f);
+  const float x0 = xmin - margin, y0 = ymin - margin;
+  const int gx = std::max(1, (int)std::floor((xmax + margin - x0) / cell) + 1);
+  const int gy = std::max(1, (int)std::floor((ymax + margin - y0) / cell) + 1);
+  std::vector<std::vector<uint16_t>> cells((size_t)gx * gy);
+  const float inv = 1.0f / cell;
+  for (int i = 0; i < n_seg; ++i) {
+    const float* s = segments + 4 * i;
+    const float sx0 = std::min(s[0], s[2]) - margin, sx1 = std::max(s[0], s[2]) + margin;
+    const float sy0 = std::min(s[1], s[3]) - margin, sy1 = std::max(s[1], s[3]) + margin;
+    int cx0 = std::max(0, (int)std::floor((sx0 - x0) * inv) - 0), cx1 = std::min(gx - 1, (int)std::floor((sx1 - x0) * inv));
+    int cy0 = std::max(0, (int)std::floor((sy0 - y0) * inv) - 0), cy1 = std::min(gy - 1, (int)std::floor((sy1 - y0) * inv));
+    for (int cy = cy0; cy <= cy1; ++cy)
+      for (int cx = cx0; cx <= cx1; ++cx) {
+        // exact-enough cull: does the segment's line pass within the (grown) cell box?
+        const float bx0 = x0 + cx * cell - margin, bx1 = x0 + (cx + 1) * cell + margin;
+        const float by0 = y0 + cy * cell - margin, by1 = y0 + (cy + 1) * cell + margin;
+        const double dx = (double)s[2] - s[0], dy = (double)s[3] - s[1];
+        const double hx = 0.5 * ((double)bx1 - bx0), hy = 0.5 * ((double)by1 - by0);
+        const double mx = 0.5 * ((double)bx1 + bx0), my = 0.5 * ((double)by1 + by0);
+        const double cr = std::fabs(((double)s[0] - mx) * dy - ((double)s[1] - my) * dx);
+        if (cr > hx * std::fabs(dy) + hy * std::fabs(dx) + 1e-6 * (std::fabs(dx) + std::fabs(dy) + 1.0)) continue;
+        cells[(size_t)cy * gx + cx].push_back((uint16_t)i);
+      }
+  }
+  size_t n_items = 0;
+  for (auto& v : cells) n_items += v.size();
+  MapHeader mh{};
+  mh.n_seg = n_seg; mh.gx = gx; mh.gy = gy; mh.n_items = (int)n_items;
+  mh.x0 = x0; mh.y0 = y0; mh.inv_cell = inv; mh.cell = cell;
+  auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  mh.off_seg = 64;
+  mh.off_cell = (uint32_t)up16(mh.off_seg + (size_t)n_seg * 16);
+  mh.off_items = (uint32_t)up16(mh.off_cell + ((size_t)gx * gy + 1) * 4);
+  mh.total_bytes = (uint32_t)up16(mh.off_items + n_items * 2);
+  std::vector<unsigned char> blob(mh.total_bytes, 0);
+  memcpy(blob.data(), &mh, sizeof(mh));
+  memcpy(blob.data() + mh.off_seg, segments, (size_t)n_seg * 16);
+  uint32_t* cs = reinterpret_cast<uint32_t*>(blob.data() + mh.off_cell);
+  uint16_t* it = reinterpret_cast<uint16_t*>(blob.data() + mh.off_items);
+  uint32_t acc = 0;
+  for (size_t ci = 0; ci < cells.size(); ++ci) {
+    cs[ci] = acc;
+    for (uint16_t s : cells[ci]) it[acc++] = s;
+  }
+  cs[cells.size()] = acc;
+  CUDA_TRY(cudaMalloc(&c->d_map, mh.total_bytes));
+  CUDA_TRY(cudaMemcpy(c->d_map, blob.data(), mh.total_bytes, cudaMemcpyHostToDevice));
+  c->map_bytes = (int)mh.total_bytes;
+  return T2D_OK;
+}
+
+int t2d_bind_state(t2d_ctx* c, float* x, float* y, float* heading, float* speed, float* vx, float* vy,
+                   const uint8_t* type_id, int32_t* step_count) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!x || !y || !heading || !speed || !vx || !vy || !type_id || !step_count)
+    return fail(T2D_E_INVALID, "t2d_bind_state: NULL array");
+  c->x = x; c->y = y; c->h = heading; c->v = speed; c->vx = vx; c->vy = vy;
+  c->type_id = type_id; c->step_count = step_count;
+  return T2D_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
+                       uint8_t* scn_status, uint8_t* done, void* stream, int do_physics) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
+  if (!c->d_table || c->n_types == 0) return fail(T2D_E_STATE, "type table not set: call t2d_set_type_table first");
+  if (do_physics && !action) return fail(T2D_E_INVALID, "action is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  StepArgs A{};
+  A.x = c->x; A.y = c->y; A.h = c->h; A.v = c->v; A.vx = c->vx; A.vy = c->vy;
+  A.type_id = c->type_id; A.step_count = c->step_count;
+  A.action = action; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
+  A.scn_status = scn_status; A.done = done;
+  A.map_blob = c->d_map; A.map_bytes = c->map_bytes;
+  A.map_in_smem = (c->d_map && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
+  A.table = c->d_table; A.n_types = c->n_types;
+  A.N = c->N; A.M = c->M; A.G = c->G;
+  const int delta_t = std::min(c->cfg.delta_t_ms, c->cfg.interval_ms);
+  A.n_steps = c->cfg.interval_ms / delta_t;                       // single_track_kinematics.py:129
+  A.dt = (float)((double)delta_t / 1000.0);                      // :128
+  A.dt_rem = (float)((double)(c->cfg.interval_ms % delta_t) / 1000.0);   // :130,152
+  A.dt_d = (double)delta_t / 1000.0;
+  A.dt_rem_d = (double)(c->cfg.interval_ms % delta_t) / 1000.0;
+  A.interval_d = (double)c->cfg.interval_ms / 1000.0;                  // point_mass.py:86
+  A.max_step = c->cfg.max_step; A.cfg_flags = c->cfg.flags;
+  A.do_physics = do_physics; A.has_bounds = c->has_bounds ? 1 : 0;
+  A.bxmin = c->bounds[0]; A.bxmax = c->bounds[1]; A.bymin = c->bounds[2]; A.bymax = c->bounds[3];
+  A.needs_vel_in = c->has_pointmass ? 1 : 0;
+  bool vec = (c->M % 4 == 0) && aligned16(A.x) && aligned16(A.y) && aligned16(A.h) && aligned16(A.v) && aligned16(A.vx) &&
+             aligned16(A.vy) && (reinterpret_cast<uintptr_t>(A.type_id) % 4 == 0) && (!action || aligned16(action)) &&
+             (!flags || reinterpret_cast<uintptr_t>(flags) % 4 == 0) && (!hit_index || reinterpret_cast<uintptr_t>(hit_index) % 8 == 0) &&
+             (!hit_segment || reinterpret_cast<uintptr_t>(hit_segment) % 8 == 0);
+  A.vec_ok = vec ? 1 : 0;
+
+  const int table_bytes = ((c->n_types * (int)sizeof(Params) + 15) / 16) * 16;
+  const int smem = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 2 * WARPS_PER_CTA * POSE_PER_WARP * (int)sizeof(float4) + 16;
+  if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");
+  if (smem != c->configured_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(t2d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    c->configured_smem = smem;
+  }
+  const int spw = 32 / c->G;
+  const long long tiles = ((long long)c->N + spw - 1) / spw;
+  const long long ctas_needed = (tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  int per_sm = 2;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2d_step_kernel, CTA_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long resident = (long long)c->sm_count * per_sm;
+  const int grid = (int)std::max(1LL, std::min(ctas_needed, resident));
+  t2d_step_kernel<<<grid, CTA_THREADS, smem, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+int t2d_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, uint8_t* scn_status,
+             uint8_t* done, void* stream) {
+  return launch_step(c, action, flags, hit_index, hit_segment, scn_status, done, stream, 1);
+}
+
+int t2d_check_events(t2d_ctx* c, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, void* stream) {
+  return launch_step(c, nullptr, flags, hit_index, hit_segment, nullptr, nullptr, stream, 0);
+}
+
+int t2d_reset(t2d_ctx* c, const uint8_t* mask, const int32_t* pool_index, int n_pool, const float* pool_x, const float* pool_y,
+              const float* pool_heading, const float* pool_speed, const float* pool_vx, const float* pool_vy, void* stream) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
+  if (!mask || !pool_x || !pool_y || !pool_heading || !pool_speed) return fail(T2D_E_INVALID, "t2d_reset: NULL array");
+  if (n_pool <= 0) return fail(T2D_E_INVALID, "n_pool must be > 0");
+  CUDA_TRY(cudaSetDevice(c->device));
+  ResetArgs A{};
+  A.x = c->x; A.y = c->y; A.h = c->h; A.v = c->v; A.vx = c->vx; A.vy = c->vy; A.step_count = c->step_count;
+  A.mask = mask; A.pool_index = pool_index;
+  A.px = pool_x; A.py = pool_y; A.ph = pool_heading; A.pv = pool_speed; A.pvx = pool_vx; A.pvy = pool_vy;
+  A.N = c->N; A.M = c->M; A.n_pool = n_pool;
+  const long long total = (long long)c->N * c->M;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
+  t2d_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+int t2d_physics_step(int device, const t2d_type_params* params, int interval_ms, int delta_t_ms, int n, float* x, float* y,
+                     float* heading, float* speed, float* vx, float* vy, const float* action, float* applied, void* stream) {
+  if (!params) return fail(T2D_E_INVALID, "params is NULL");
+  if (n < 0) return fail(T2D_E_INVALID, "n must be >= 0");
+  if (n == 0) return T2D_OK;
+  if (!x || !y || !heading || !speed || !vx || !vy || !action) return fail(T2D_E_INVALID, "t2d_physics_step: NULL array");
+  if (interval_ms <= 0 || delta_t_ms <= 0) return fail(T2D_E_INVALID, "interval_ms and delta_t_ms must be > 0");
+  if (params->model < 0 || params->model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "unknown model id");
+  CUDA_TRY(cudaSetDevice(device));
+  PhysArgs A{};
+  memcpy(&A.p, params, sizeof(Params));
+  A.x = x; A.y = y; A.h = heading; A.v = speed; A.vx = vx; A.vy = vy; A.action = action; A.applied = applied;
+  A.n = n;
+  const int delta_t = std::min(delta_t_ms, interval_ms);
+  A.n_steps = interval_ms / delta_t;
+  A.dt = (float)((double)delta_t / 1000.0);
+  A.dt_rem = (float)((double)(interval_ms % delta_t) / 1000.0);
+  A.dt_d = (double)delta_t / 1000.0;
+  A.dt_rem_d = (double)(interval_ms % delta_t) / 1000.0;
+  A.interval_d = (double)interval_ms / 1000.0;
+  const int grid = std::min((n + 255) / 256, 148 * 8);
+  t2d_physics_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,455 @@
+// t2d_math.cuh - per-participant physics and per-pair predicates of the batched tick.
+//
+// Everything here is a pure function of its arguments so that the same source is
+//   * inlined into the sm_100a kernels (t2d_kernels.cu), and
+//   * compiled by g++ into tests/hostsim (a unit-test harness that checks this arithmetic
+//     against the float64 oracle without a GPU; it is NOT a product fallback).
+//
+// Arithmetic policy (DESIGN.md "numerics"):
+//   * SingleTrackKinematics: fp32.  The reference's n Euler sub-steps are reproduced as the
+//     same discrete sums, but (cos, sin)(phi+beta) is advanced by an angle-addition rotation
+//     with a short polynomial for the small increment, and the position / heading sums are
+//     accumulated separately and added to the state once (one rounding at |x| scale).
+//   * SingleTrackDynamics: fp64 (the yaw/slip ODE is stiff below ~0.4 m/s, explicit Euler
+//     amplifies rounding by up to (0.745/v - 1)^20 there; B200 issues DFMA at half FFMA rate).
+//   * PointMass: fp64 arithmetic on the fp32 state (a few dozen flops).
+//   * Collision predicates: fp32 with a forward error bound ("filtered predicate"); a pair
+//     whose margin is inside the bound is re-evaluated exactly as the float64 oracle does
+//     (double trig of the fp32 heading), so flags are bit-exact against the oracle.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define T2D_HD __host__ __device__ __forceinline__
+#define T2D_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define T2D_HD inline
+#define T2D_HD_NOINLINE
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define T2D_RSQRTF(x) rsqrtf(x)
+#else
+#define T2D_RSQRTF(x) (1.0f / sqrtf(x))
+#endif
+
+namespace t2d {
+
+constexpr int MODEL_KINEMATICS = 0;
+constexpr int MODEL_DYNAMICS = 1;
+constexpr int MODEL_POINTMASS_NEWTON = 2;
+constexpr int MODEL_POINTMASS_EULER = 3;
+constexpr int MODEL_STATIC = 4;
+constexpr int SHAPE_OBB = 0;
+constexpr int SHAPE_CIRCLE = 1;
+constexpr int SHAPE_NONE = 2;
+
+constexpr float TWO_PI_HI = 6.2831854820251465f;   // fp32(2*pi)  ( > 2*pi )
+constexpr float TWO_PI_LO = -1.7484555e-7f;        // 2*pi - TWO_PI_HI
+constexpr float INV_TWO_PI = 0.15915494309189535f;
+constexpr double TWO_PI_D = 6.283185307179586476925286766559;
+constexpr double G_ACC = 9.81;                     // physics_model_base.py:25
+
+// Mirror of t2d_type_params (include/t2d_b200.h); 19 words.
+struct Params {
+  float half_len, half_wid, radius, lf, lr;
+  float steer_lo, steer_hi, speed_lo, speed_hi, accel_lo, accel_hi;
+  float mass, mass_height, mu, I_z, cf, cr;
+  int32_t model, shape;
+};
+
+T2D_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // np.clip
+T2D_HD double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// np.mod(phi, 2*pi) for an fp32 angle: result in [0, 2*pi) (Cody-Waite two-term reduction).
+T2D_HD float wrap_two_pi(float phi) {
+  float q = floorf(phi * INV_TWO_PI);
+  float r = fmaf(-q, TWO_PI_HI, phi);
+  r = fmaf(-q, TWO_PI_LO, r);
+  if (r < 0.0f) r += TWO_PI_HI;
+  if (r >= TWO_PI_HI) r -= TWO_PI_HI;
+  if (r < 0.0f) r = 0.0f;
+  return r;
+}
+
+// (cos, sin) of a small angle d, |d| <= 0.25: Taylor, abs error < 2e-9 / 1.3e-8 relative.
+T2D_HD void small_sincos(float d, float& sn, float& hv /* 1 - cos */) {
+  float d2 = d * d;
+  sn = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -1.6666667e-1f), 1.0f);
+  hv = d2 * fmaf(d2, fmaf(d2, 1.3888889e-3f, -4.1666667e-2f), 0.5f);
+}
+
+// ------------------------------------------------------------------------------------------
+// SingleTrackKinematics.step/_step  (single_track_kinematics.py:178-198,126-176), W lanes of
+// independent participants advanced together (instruction-level parallelism for the serial
+// Euler chain).
+// ------------------------------------------------------------------------------------------
+template <int W>
+struct KinIO {
+  float x[W], y[W], h[W], v[W];   // in: state; out: new state (heading wrapped to [0, 2pi))
+  float vx[W], vy[W];             // out: v*(cos, sin)(phi)                         :170-171
+  float ch[W], sh[W];             // out: (cos, sin)(new heading) for the pose
+  float acc[W], steer[W];         // in: raw action; out: clipped action            :192-193
+};
+
+template <int W>
+T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_steps, float dt, float dt_rem) {
+  float c[W], s[W], v[W], Sx[W], Sy[W], Sv[W], k[W], a[W], vlo[W], vhi[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    a[i] = clampf(io.acc[i], p[i]->accel_lo, p[i]->accel_hi);       // :192
+    float d = clampf(io.steer[i], p[i]->steer_lo, p[i]->steer_hi);  // :193
+    io.acc[i] = a[i];
+    io.steer[i] = d;
+    float L = p[i]->lf + p[i]->lr;                                  // :85
+    float sd, cd;
+    sincosf(d, &sd, &cd);
+    float tan_d = sd / cd;
+    float tb = p[i]->lr / L * tan_d;          // tan(beta), beta = atan(lr/L tan delta)  :127
+    float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
+    float sb = tb * cb;                          // sin(beta)
+    k[i] = tan_d * cb / L;                       // dphi = v * k                           :141
+    float sp, cp;
+    sincosf(io.h[i], &sp, &cp);
+    c[i] = cp * cb - sp * sb;                    // cos(phi + beta)
+    s[i] = sp * cb + cp * sb;                    // sin(phi + beta)
+    v[i] = io.v[i];
+    vlo[i] = p[i]->speed_lo;
+    vhi[i] = p[i]->speed_hi;
+    Sx[i] = 0.0f; Sy[i] = 0.0f; Sv[i] = 0.0f;
+  }
+  // main sub-steps :137-148 ; derivatives from the OLD (phi, v), then v clipped
+  for (int it = 0; it < n_steps; ++it) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      Sx[i] = fmaf(v[i], c[i], Sx[i]);
+      Sy[i] = fmaf(v[i], s[i], Sy[i]);
+      Sv[i] += v[i];
+      float d = k[i] * dt * v[i];
+      float sn, hv;
+      if (fabsf(d) <= 0.25f) {
+        small_sincos(d, sn, hv);
+      } else {  // unconstrained speed ranges only
+        float cs;
+        sincosf(d, &sn, &cs);
+        hv = 1.0f - cs;
+      }
+      float c2 = c[i] - fmaf(c[i], hv, s[i] * sn);
+      float s2 = s[i] - fmaf(s[i], hv, -c[i] * sn);
+      c[i] = c2;
+      s[i] = s2;
+      v[i] = clampf(fmaf(a[i], dt, v[i]), vlo[i], vhi[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    float x = fmaf(dt, Sx[i], io.x[i]);
+    float y = fmaf(dt, Sy[i], io.y[i]);
+    float dphi = k[i] * dt * Sv[i];
+    if (dt_rem > 0.0f) {  // remainder sub-step :151-163
+      x = fmaf(dt_rem * v[i], c[i], x);
+      y = fmaf(dt_rem * v[i], s[i], y);
+      dphi = fmaf(k[i] * dt_rem, v[i], dphi);
+      v[i] = clampf(fmaf(a[i], dt_rem, v[i]), vlo[i], vhi[i]);
+    }
+    float hn = wrap_two_pi(io.h[i] + dphi);     // np.mod(phi, 2 pi)                        :169
+    float sh, ch;
+    sincosf(hn, &sh, &ch);
+    io.x[i] = x; io.y[i] = y; io.h[i] = hn; io.v[i] = v[i];
+    io.vx[i] = v[i] * ch;                        // v cos(phi), no beta                    :170
+    io.vy[i] = v[i] * sh;                        //                                        :171
+    io.ch[i] = ch; io.sh[i] = sh;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SingleTrackDynamics.step/_step  (single_track_dynamics.py:231-251,140-229), fp64.
+// No remainder sub-step (the reference computes `remainder` at :143 and never uses it).
+// ------------------------------------------------------------------------------------------
+struct OneIO {
+  float x, y, h, v, vx, vy;  // state in / out
+  float ch, sh;              // out: (cos, sin)(new heading)
+  float a0, a1;              // in: raw action; out: applied action
+};
+
+T2D_HD void dynamics_step(OneIO& io, const Params& p, int n_steps, double dt) {
+  const double lf = p.lf, lr = p.lr, L = (double)p.lf + (double)p.lr;
+  const double accel = clampd(io.a0, p.accel_lo, p.accel_hi);   // :245
+  const double delta = clampd(io.a1, p.steer_lo, p.steer_hi);   // :246
+  io.a0 = (float)accel;
+  io.a1 = (float)delta;
+  const double mass = p.mass, h = p.mass_height, mu = p.mu, Iz = p.I_z, cf = p.cf, cr = p.cr;
+  const double factor_f = (G_ACC * lr - accel * h) / L;          // :145
+  const double factor_r = (G_ACC * lf + accel * h) / L;          // :146
+  const double lf_cf_f = lf * cf * factor_f, lr_cr_r = lr * cr * factor_r;      // :149-150
+  const double lf2_cf_f = lf * lf * cf * factor_f, lr2_cr_r = lr * lr * cr * factor_r;
+  const double cf_f = cf * factor_f, cr_r = cr * factor_r;
+  const double tan_d = tan(delta);
+  const double cos_d = cos(delta);
+  double x = io.x, y = io.y, phi = io.h, v = io.v;
+  double d_phi = v / L * tan_d;                                  // :159
+  double beta = atan(lr / lf * tan_d);                           // :160 (lr/lf, not lr/L)
+  const double vlo = p.speed_lo, vhi = p.speed_hi;
+  const double d_beta_slow = lr / ((1.0 + tan_d * lr / L) * (1.0 + tan_d * lr / L)) / L / (cos_d * cos_d) * delta;  // :194-200
+  for (int it = 0; it < n_steps; ++it) {                          // :163-218
+    double sn, cs;
+    sincos(phi + beta, &sn, &cs);
+    const double dx = v * cs, dy = v * sn;
+    const double v_safe = fabs(v) > 1e-6 ? v : (v >= 0.0 ? 1e-6 : -1e-6);  // :169
+    double d_beta;
+    if (fabs(v) >= 0.1) {                                         // :171
+      const double dd_phi = mu * mass / Iz * (lf_cf_f * delta + (lr_cr_r - lf_cf_f) * beta - (lf2_cf_f + lr2_cr_r) * d_phi / v_safe);
+      d_beta = mu / v_safe * (cf_f * delta - (cr_r + cf_f) * beta + (lr_cr_r - lf_cf_f) * d_phi / v_safe) - d_phi;
+      d_phi += dd_phi * dt;                                       // :192
+    } else {
+      d_beta = d_beta_slow;
+      d_phi += v * cos(beta) / L * tan_d * dt;                    // :210
+    }
+    x += dx * dt;                                                 // :212-216
+    y += dy * dt;
+    v += accel * dt;
+    phi += d_phi * dt;
+    beta += d_beta * dt;
+    v = clampd(v, vlo, vhi);                                      // :218
+  }
+  double hd = fmod(phi, TWO_PI_D);                               // np.mod(phi, 2 pi) :224
+  if (hd < 0.0) hd += TWO_PI_D;
+  float hn = (float)hd;
+  if (hn >= TWO_PI_HI) hn = 0.0f;
+  float sh, ch;
+  sincosf(hn, &sh, &ch);
+  io.x = (float)x; io.y = (float)y; io.h = hn; io.v = (float)v;
+  io.vx = io.v * ch; io.vy = io.v * sh;      // State.velocity of a State without vx, vy (state.py:160-165)
+  io.ch = ch; io.sh = sh;
+}
+
+// ------------------------------------------------------------------------------------------
+// PointMass.step  (point_mass.py:209-232).  The acceleration is NOT clipped (:222-225 computes
+// a clipped magnitude and drops it).  Input velocity = (vx, vy); heading = atan2(new velocity).
+// ------------------------------------------------------------------------------------------
+T2D_HD double pm_t1(double ax, double ay, double vx, double vy, double lim, double sign, double dt) {
+  const double a_ = ax * ax + ay * ay;                    // :106-108 / :141-143
+  const double b_ = 2.0 * (ax * vx + ay * vy);
+  const double c_ = vx * vx + vy * vy - lim * lim;
+  double t1;
+  if (fabs(a_) < 1e-12) {
+    t1 = fabs(b_) < 1e-12 ? 0.0 : -c_ / b_;               // :111-118
+  } else {
+    const double disc = fmax(0.0, b_ * b_ - 4.0 * a_ * c_);
+    t1 = (-b_ + sign * sqrt(disc)) / (2.0 * a_);          // :124 (-) / :159 (+)
+  }
+  return clampd(t1, 0.0, dt);                             // :127
+}
+
+T2D_HD void pointmass_newton_step(OneIO& io, const Params& p, double dt) {
+  const double ax = io.a0, ay = io.a1, vx = io.vx, vy = io.vy;
+  const double nvx = vx + ax * dt, nvy = vy + ay * dt;    // :88-89
+  const double nsp = sqrt(nvx * nvx + nvy * nvy);
+  const double slo = p.speed_lo, shi = p.speed_hi;
+  double x, y, ovx, ovy;
+  if (slo <= nsp && nsp <= shi) {                          // :93-101
+    x = (double)io.x + vx * dt + 0.5 * ax * dt * dt;
+    y = (double)io.y + vy * dt + 0.5 * ay * dt * dt;
+    ovx = nvx; ovy = nvy;
+  } else {
+    const bool low = nsp < slo;                            // :105 else :140
+    const double t1 = pm_t1(ax, ay, vx, vy, low ? slo : shi, low ? -1.0 : 1.0, dt);
+    const double t2 = dt - t1;
+    ovx = vx + ax * t1; ovy = vy + ay * t1;
+    x = (double)io.x + vx * t1 + 0.5 * ax * t1 * t1 + ovx * t2;
+    y = (double)io.y + vy * t1 + 0.5 * ay * t1 * t1 + ovy * t2;
+  }
+  io.x = (float)x; io.y = (float)y;
+  io.vx = (float)ovx; io.vy = (float)ovy;
+  io.h = (float)atan2(ovy, ovx);
+  io.v = (float)sqrt(ovx * ovx + ovy * ovy);               // State.speed (state.py:143-146)
+  sincosf(io.h, &io.sh, &io.ch);
+}
+
+T2D_HD void pointmass_euler_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem) {
+  const double ax = io.a0, ay = io.a1;                     // point_mass.py:177-207
+  double vx = io.vx, vy = io.vy, x = io.x, y = io.y, heading = io.h;
+  const double slo = p.speed_lo, shi = p.speed_hi;
+  const int total = n_steps + (dt_rem > 0.0 ? 1 : 0);
+  for (int it = 0; it < total; ++it) {
+    const double h = it < n_steps ? dt : dt_rem;
+    vx += ax * h;
+    vy += ay * h;
+    const double sp = sqrt(vx * vx + vy * vy);
+    const double cl = clampd(sp, slo, shi);
+    if (fabs(sp - cl) > 1e-12) {                           // :195
+      vx = cl * cos(heading);
+      vy = cl * sin(heading);
+    }
+    x += vx * h;
+    y += vy * h;
+    heading = atan2(vy, vx);
+  }
+  io.x = (float)x; io.y = (float)y; io.h = (float)heading;
+  io.vx = (float)vx; io.vy = (float)vy;
+  io.v = (float)sqrt(vx * vx + vy * vy);
+  sincosf(io.h, &io.sh, &io.ch);
+}
+
+// ==========================================================================================
+// Closed-set predicates.  *_f32 return 1 (intersects), 0 (disjoint) or -1 (inside the fp32
+// error bound: caller must ask the *_f64 twin).  *_f64 evaluate exactly the float64 formulas
+// of oracle/geometry.py on the fp32 inputs.
+// Pose of an OBB: centre (x, y), (c, s) = (cos, sin) heading, half extents (l, w).
+// ==========================================================================================
+constexpr float EPS_LIN = 2e-6f;  // >= 4x the forward error of the fp32 evaluation, relative to the magnitudes summed
+
+T2D_HD int obb_obb_f32(float xa, float ya, float ca, float sa, float la, float wa,
+                       float xb, float yb, float cb, float sb, float lb, float wb) {
+  const float tx = xb - xa, ty = yb - ya;
+  const float c = fmaf(ca, cb, sa * sb), s = fmaf(ca, sb, -sa * cb);
+  const float ac = fabsf(c), as = fabsf(s);
+  const float m0 = fabsf(fmaf(tx, ca, ty * sa)) - (la + fmaf(lb, ac, wb * as));
+  const float m1 = fabsf(fmaf(ty, ca, -tx * sa)) - (wa + fmaf(lb, as, wb * ac));
+  const float m2 = fabsf(fmaf(tx, cb, ty * sb)) - (lb + fmaf(la, ac, wa * as));
+  const float m3 = fabsf(fmaf(ty, cb, -tx * sb)) - (wb + fmaf(la, as, wa * ac));
+  const float e = EPS_LIN * (fabsf(tx) + fabsf(ty) + la + wa + lb + wb);
+  const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  if (mx > e) return 0;
+  if (mx < -e) return 1;
+  return -1;
+}
+
+T2D_HD bool obb_obb_f64(double xa, double ya, double ha, double la, double wa,
+                        double xb, double yb, double hb, double lb, double wb) {
+  double sa, ca, sb, cb;
+  sincos(ha, &sa, &ca);
+  sincos(hb, &sb, &cb);
+  const double tx = xb - xa, ty = yb - ya;
+  const double c = ca * cb + sa * sb, s = ca * sb - sa * cb;
+  const double ac = fabs(c), as = fabs(s);
+  return fabs(tx * ca + ty * sa) <= la + (lb * ac + wb * as) &&
+         fabs(ty * ca - tx * sa) <= wa + (lb * as + wb * ac) &&
+         fabs(tx * cb + ty * sb) <= lb + (la * ac + wa * as) &&
+         fabs(ty * cb - tx * sb) <= wb + (la * as + wa * ac);
+}
+
+T2D_HD int obb_circle_f32(float xa, float ya, float ca, float sa, float la, float wa,
+                          float xc, float yc, float r) {
+  const float tx = xc - xa, ty = yc - ya;
+  const float qx = fabsf(fmaf(tx, ca, ty * sa)) - la;
+  const float qy = fabsf(fmaf(ty, ca, -tx * sa)) - wa;
+  const float dx = fmaxf(qx, 0.0f), dy = fmaxf(qy, 0.0f);
+  const float m = fmaf(dx, dx, dy * dy) - r * r;
+  const float e1 = EPS_LIN * (fabsf(tx) + fabsf(ty) + la + wa + r);
+  const float e = fmaf(2.0f * e1, dx + dy + r, e1 * e1);
+  if (m > e) return 0;
+  if (m < -e) return 1;
+  return -1;
+}
+
+T2D_HD bool obb_circle_f64(double xa, double ya, double ha, double la, double wa,
+                           double xc, double yc, double r) {
+  double sa, ca;
+  sincos(ha, &sa, &ca);
+  const double tx = xc - xa, ty = yc - ya;
+  const double qx = fabs(tx * ca + ty * sa) - la;
+  const double qy = fabs(ty * ca - tx * sa) - wa;
+  const double dx = fmax(qx, 0.0), dy = fmax(qy, 0.0);
+  return dx * dx + dy * dy <= r * r;
+}
+
+T2D_HD int circle_circle_f32(float xa, float ya, float ra, float xb, float yb, float rb) {
+  const float tx = xb - xa, ty = yb - ya;
+  const float d2 = fmaf(tx, tx, ty * ty), rr = (ra + rb) * (ra + rb);
+  const float e = 4.0f * EPS_LIN * (d2 + rr);
+  const float m = d2 - rr;
+  if (m > e) return 0;
+  if (m < -e) return 1;
+  return -1;
+}
+
+T2D_HD bool circle_circle_f64(double xa, double ya, double ra, double xb, double yb, double rb) {
+  const double tx = xb - xa, ty = yb - ya;
+  return tx * tx + ty * ty <= (ra + rb) * (ra + rb);
+}
+
+T2D_HD int obb_segment_f32(float xa, float ya, float ca, float sa, float la, float wa,
+                           float x1, float y1, float x2, float y2) {
+  const float ux = x1 - xa, uy = y1 - ya, vx = x2 - xa, vy = y2 - ya;
+  const float p1x = fmaf(ux, ca, uy * sa), p1y = fmaf(uy, ca, -ux * sa);
+  const float p2x = fmaf(vx, ca, vy * sa), p2y = fmaf(vy, ca, -vx * sa);
+  const float dx = p2x - p1x, dy = p2y - p1y;
+  const float e1 = EPS_LIN * (fabsf(ux) + fabsf(uy) + fabsf(vx) + fabsf(vy) + la + wa);
+  const float m0 = -la - fmaxf(p1x, p2x);
+  const float m1 = fminf(p1x, p2x) - la;
+  const float m2 = -wa - fmaxf(p1y, p2y);
+  const float m3 = fminf(p1y, p2y) - wa;
+  const float mb = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  const float m4 = fabsf(fmaf(p1x, dy, -p1y * dx)) - fmaf(la, fabsf(dy), wa * fabsf(dx));
+  const float e4 = 2.0f * e1 * (fabsf(dx) + fabsf(dy) + fabsf(p1x) + fabsf(p1y) + la + wa);
+  if (mb > e1 || m4 > e4) return 0;
+  if (mb < -e1 && m4 < -e4) return 1;
+  return -1;
+}
+
+T2D_HD bool obb_segment_f64(double xa, double ya, double ha, double la, double wa,
+                            double x1, double y1, double x2, double y2) {
+  double sa, ca;
+  sincos(ha, &sa, &ca);
+  const double ux = x1 - xa, uy = y1 - ya, vx = x2 - xa, vy = y2 - ya;
+  const double p1x = ux * ca + uy * sa, p1y = uy * ca - ux * sa;
+  const double p2x = vx * ca + vy * sa, p2y = vy * ca - vx * sa;
+  const double dx = p2x - p1x, dy = p2y - p1y;
+  return fmax(p1x, p2x) >= -la && fmin(p1x, p2x) <= la && fmax(p1y, p2y) >= -wa && fmin(p1y, p2y) <= wa &&
+         fabs(p1x * dy - p1y * dx) <= la * fabs(dy) + wa * fabs(dx);
+}
+
+T2D_HD int circle_segment_f32(float xc, float yc, float r, float x1, float y1, float x2, float y2) {
+  const float dx = x2 - x1, dy = y2 - y1, ux = xc - x1, uy = yc - y1;
+  const float dd = fmaf(dx, dx, dy * dy);
+  float t = dd > 0.0f ? fmaf(ux, dx, uy * dy) / dd : 0.0f;
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float ex = fmaf(-t, dx, ux), ey = fmaf(-t, dy, uy);
+  const float d2 = fmaf(ex, ex, ey * ey);
+  const float m = d2 - r * r;
+  const float e1 = 2.0f * EPS_LIN * (fabsf(ux) + fabsf(uy) + fabsf(dx) + fabsf(dy) + r);
+  const float e = fmaf(2.0f * e1, sqrtf(d2) + r, e1 * e1);
+  if (m > e) return 0;
+  if (m < -e) return 1;
+  return -1;
+}
+
+T2D_HD bool circle_segment_f64(double xc, double yc, double r, double x1, double y1, double x2, double y2) {
+  const double dx = x2 - x1, dy = y2 - y1, ux = xc - x1, uy = yc - y1;
+  const double dd = dx * dx + dy * dy;
+  double t = dd > 0.0 ? (ux * dx + uy * dy) / dd : 0.0;
+  t = fmin(fmax(t, 0.0), 1.0);
+  const double ex = ux - t * dx, ey = uy - t * dy;
+  return ex * ex + ey * ey <= r * r;
+}
+
+// OutBound.update (out_bound.py:37-48): pose not inside the closed box <=> some corner strictly
+// outside.  (ex, ey) = half sizes of the pose's axis-aligned box.  bounds = xmin, xmax, ymin, ymax.
+T2D_HD int out_of_bound_f32(float x, float y, float c, float s, float l, float w, bool circle,
+                            float xmin, float xmax, float ymin, float ymax) {
+  const float ex = circle ? l : fmaf(l, fabsf(c), w * fabsf(s));
+  const float ey = circle ? l : fmaf(l, fabsf(s), w * fabsf(c));
+  const float a0 = x - xmin, a1 = xmax - x, a2 = y - ymin, a3 = ymax - y;
+  const float m = fmaxf(fmaxf(ex - a0, ex - a1), fmaxf(ey - a2, ey - a3));  // > 0 <=> out
+  const float e = EPS_LIN * (fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(a2), fabsf(a3))) + l + w);
+  if (m > e) return 1;
+  if (m < -e) return 0;
+  return -1;
+}
+
+T2D_HD bool out_of_bound_f64(double x, double y, double h, double l, double w, bool circle,
+                             double xmin, double xmax, double ymin, double ymax) {
+  double ex = l, ey = l;
+  if (!circle) {
+    double s, c;
+    sincos(h, &s, &c);
+    ex = l * fabs(c) + w * fabs(s);
+    ey = l * fabs(s) + w * fabs(c);
+  }
+  return (x - ex < xmin) || (x + ex > xmax) || (y - ey < ymin) || (y + ey > ymax);
+}
+
+}  // namespace t2d

@@ -1,0 +1,198 @@
+"""BatchedWorld: N scenarios x M participants of structure-of-arrays state in HBM.
+
+This is the object behind the reference-shaped facades (``physics``, ``traffic``, ``envs``): it
+owns the fp32 SoA tensors, the C-ABI context, and forwards ``step`` / ``check_events`` / ``reset``
+to the sm_100a kernels.  PyTorch is only the device-memory container (``tensor.data_ptr()``) and
+the stream provider; there is no eager/CPU implementation behind it.
+
+Replaces the per-object loop of the reference tick: ``ScenarioManager.update`` ->
+``physics_model.step`` -> ``agent.add_state`` -> ``check_status`` (envs/parking.py:352-392).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .types import TYPE_INACTIVE, TypeTable
+
+CFG_ANY_PARTICIPANT = 1
+CFG_STEER_FIRST = 2
+
+F_DYNAMIC, F_STATIC, F_OUTBOUND = 1, 2, 4
+
+
+@dataclass
+class StepResult:
+    """Device tensors written by one ``step`` (views of buffers owned by the world)."""
+
+    flags: torch.Tensor        # uint8 [N, M]: bit0 dynamic collision, bit1 static collision, bit2 out of bound
+    hit_index: torch.Tensor    # int16 [N, M]: lowest colliding participant index or -1
+    hit_segment: torch.Tensor  # int16 [N, M]: lowest colliding map segment index or -1
+    status: torch.Tensor       # uint8 [N]: ScenarioStatus
+    done: torch.Tensor         # uint8 [N]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class BatchedWorld:
+    def __init__(self, n_scenarios: int, m_participants: int, type_table: TypeTable, device="cuda:0",
+                 interval: int = 100, delta_t: int = 5, max_step: Optional[int] = None,
+                 any_participant: bool = False, steer_first: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tactics2d_b200 needs a CUDA device: the batched tick only exists as sm_100a kernels")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedWorld lives on a CUDA device")
+        self.N, self.M = int(n_scenarios), int(m_participants)
+        self.type_table = type_table
+        self.interval, self.delta_t = int(interval), int(delta_t)
+        self.max_step = int(max_step) if max_step else 0
+        self.flags_cfg = (CFG_ANY_PARTICIPANT if any_participant else 0) | (CFG_STEER_FIRST if steer_first else 0)
+        self._ctx = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dev_index = dev_index
+        cfg = _lib.Config(self.interval, self.delta_t, self.max_step, self.flags_cfg)
+        _lib.check(self.lib.t2d_create(C.byref(self._ctx), dev_index, self.N, self.M, C.byref(cfg)))
+        arr = type_table.to_c_array()
+        _lib.check(self.lib.t2d_set_type_table(self._ctx, arr, len(type_table)))
+
+        f = dict(dtype=torch.float32, device=self.device)
+        shape = (self.N, self.M)
+        self.x = torch.zeros(shape, **f)
+        self.y = torch.zeros(shape, **f)
+        self.heading = torch.zeros(shape, **f)
+        self.speed = torch.zeros(shape, **f)
+        self.vx = torch.zeros(shape, **f)
+        self.vy = torch.zeros(shape, **f)
+        self.type_id = torch.full(shape, TYPE_INACTIVE, dtype=torch.uint8, device=self.device)
+        self.step_count = torch.zeros(self.N, dtype=torch.int32, device=self.device)
+        self.frame = 0  # ms; State.frame advances by `interval` per step (single_track_kinematics.py:166)
+        self._out = StepResult(
+            flags=torch.zeros(shape, dtype=torch.uint8, device=self.device),
+            hit_index=torch.full(shape, -1, dtype=torch.int16, device=self.device),
+            hit_segment=torch.full(shape, -1, dtype=torch.int16, device=self.device),
+            status=torch.ones(self.N, dtype=torch.uint8, device=self.device),
+            done=torch.zeros(self.N, dtype=torch.uint8, device=self.device))
+        self._bind()
+        self.segments = None
+        self.bounds = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _bind(self):
+        _lib.check(self.lib.t2d_bind_state(self._ctx, _ptr(self.x), _ptr(self.y), _ptr(self.heading), _ptr(self.speed),
+                                           _ptr(self.vx), _ptr(self.vy), _ptr(self.type_id), _ptr(self.step_count)))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.t2d_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def set_config(self, interval=None, delta_t=None, max_step=None):
+        if interval is not None:
+            self.interval = int(interval)
+        if delta_t is not None:
+            self.delta_t = int(delta_t)
+        if max_step is not None:
+            self.max_step = int(max_step)
+        cfg = _lib.Config(self.interval, self.delta_t, self.max_step, self.flags_cfg)
+        _lib.check(self.lib.t2d_set_config(self._ctx, C.byref(cfg)))
+
+    def set_map(self, segments=None, bounds: Optional[Sequence[float]] = None, cell_size: float = 0.0):
+        """Static geometry of the scenario (shared by all N scenarios).
+
+        ``segments``: array [S, 4] of (x1, y1, x2, y2) collidable polyline pieces in list order -
+        what ``StaticCollision.reset(static_objects)`` receives (collision.py:45-46), flattened;
+        ``bounds``: (xmin, xmax, ymin, ymax) as ``Map.boundary`` / ``OutBound.reset`` take it
+        (out_bound.py:50-65), or None."""
+        seg = None if segments is None else np.ascontiguousarray(np.asarray(segments, dtype=np.float32).reshape(-1, 4))
+        n_seg = 0 if seg is None else seg.shape[0]
+        b = None if bounds is None else np.asarray(bounds, dtype=np.float32)
+        _lib.check(self.lib.t2d_set_map(
+            self._ctx, C.c_void_p(0 if n_seg == 0 else seg.ctypes.data), n_seg,
+            C.c_void_p(0 if b is None else b.ctypes.data), float(cell_size)))
+        self.segments = seg
+        self.bounds = None if b is None else tuple(float(v) for v in b)
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, x, y, heading, speed=None, vx=None, vy=None, type_id=None):
+        """Copy host or device arrays [N, M] into the SoA state.  Missing ``vx, vy`` are derived as
+        ``State.velocity`` does (state.py:160-165); missing ``speed`` as ``State.speed`` (:143-146)."""
+        def put(dst, src):
+            dst.copy_(torch.as_tensor(np.asarray(src) if not torch.is_tensor(src) else src).to(dst.dtype).reshape(dst.shape))
+
+        put(self.x, x); put(self.y, y); put(self.heading, heading)
+        if speed is None and (vx is None or vy is None):
+            raise ValueError("give speed, or vx and vy")
+        if vx is not None and vy is not None:
+            put(self.vx, vx); put(self.vy, vy)
+        if speed is not None:
+            put(self.speed, speed)
+        else:
+            self.speed.copy_(torch.sqrt(self.vx * self.vx + self.vy * self.vy))
+        if vx is None or vy is None:
+            self.vx.copy_(self.speed * torch.cos(self.heading))
+            self.vy.copy_(self.speed * torch.sin(self.heading))
+        if type_id is not None:
+            put(self.type_id, type_id)
+
+    def state_numpy(self) -> dict:
+        return {k: getattr(self, k).detach().cpu().numpy() for k in ("x", "y", "heading", "speed", "vx", "vy")}
+
+    # ------------------------------------------------------------------ the hot path
+    def step(self, action: torch.Tensor) -> StepResult:
+        """One tick.  ``action``: fp32 device tensor [N, M, 2] = (accel, steer) per bicycle
+        (``(steer, accel)`` when built with ``steer_first``), (ax, ay) per point mass."""
+        if action.device != self.device or action.dtype != torch.float32:
+            raise ValueError("action must be an fp32 tensor on the world's device")
+        if tuple(action.shape) != (self.N, self.M, 2) or not action.is_contiguous():
+            raise ValueError(f"action must be contiguous [{self.N}, {self.M}, 2]")
+        o = self._out
+        _lib.check(self.lib.t2d_step(self._ctx, _ptr(action), _ptr(o.flags), _ptr(o.hit_index), _ptr(o.hit_segment),
+                                     _ptr(o.status), _ptr(o.done), self._stream()))
+        self.frame += self.interval
+        return o
+
+    def check_events(self) -> StepResult:
+        """The detectors on the current poses, no physics (``EventBase.update``)."""
+        o = self._out
+        _lib.check(self.lib.t2d_check_events(self._ctx, _ptr(o.flags), _ptr(o.hit_index), _ptr(o.hit_segment), self._stream()))
+        return o
+
+    def reset(self, mask: torch.Tensor, pool: dict, pool_index: Optional[torch.Tensor] = None):
+        """Re-initialise the scenarios with ``mask[n] != 0`` from row ``pool_index[n]`` (default n)
+        of the pool arrays ``x, y, heading, speed[, vx, vy]`` [P, M] (``ScenarioManager.reset``,
+        parking.py:397-441; ``ParticipantBase.reset``, participant_base.py:236-246)."""
+        px = pool["x"]
+        n_pool = px.shape[0]
+        for k in ("x", "y", "heading", "speed"):
+            t = pool[k]
+            if t.device != self.device or t.dtype != torch.float32 or tuple(t.shape) != (n_pool, self.M):
+                raise ValueError(f"pool[{k!r}] must be fp32 [{n_pool}, {self.M}] on {self.device}")
+        if mask.dtype != torch.uint8:
+            mask = mask.to(torch.uint8)
+        if pool_index is not None and pool_index.dtype != torch.int32:
+            pool_index = pool_index.to(torch.int32)
+        if pool_index is None and n_pool < self.N:
+            raise ValueError("without pool_index the pool needs one row per scenario")
+        _lib.check(self.lib.t2d_reset(self._ctx, _ptr(mask), _ptr(pool_index), n_pool, _ptr(pool["x"]), _ptr(pool["y"]),
+                                      _ptr(pool["heading"]), _ptr(pool["speed"]), _ptr(pool.get("vx")),
+                                      _ptr(pool.get("vy")), self._stream()))
