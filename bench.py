@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py - participant-steps/s of the batched env.step() hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the fused tick (physics -> pose -> collisions -> out-of-bound -> status) over one
+batch of synthetic scenarios.  At N=1 the workload is BASELINE.json configs[1]: 4096 scenarios x 64
+participants, SingleTrackKinematics + OBB collision, synthetic grid map.  For N>1 every rank steps its own
+4096 x 64 shard (weak scaling; scenarios are independent) and the ranks exchange the done mask with one
+all-gather per step.
+
+Timing rules followed: W >= 3 warm-up steps; inputs larger than L2 - the timed steps rotate over R
+independent world replicas whose state + actions + outputs exceed the 126 MB L2 (R x 14.2 MB), so every
+step streams its state from HBM; device timing with CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks; SM clocks and throttle reasons sampled with nvidia-smi while
+the timed region is repeated.  The K-step timed region is captured in a CUDA graph (the kernels are a few
+microseconds each; a Python launch loop would measure the interpreter) and is repeated `reps` times, the
+median repetition is reported.
+
+`--impl reference` times the reference's own execution model for this path - one Python call per
+participant with NumPy scalar float64 arithmetic and per-pose predicate loops (oracle/scalar_port.py, a
+restatement: the reference's shapely/gymnasium dependencies are not installable here) - on all host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "participant_steps_per_sec"
+UNIT = "participant-steps/s"
+N_SCN, M_PART = 4096, 64
+
+# algorithmic bytes per participant-step of the fused kernel (DESIGN.md "Roofline"): reads x, y, heading,
+# speed (16) + action (8) + type id (1); writes x, y, heading, speed, vx, vy (24) + event byte (1) +
+# hit_index (2) + hit_segment (2); per scenario step_count r/w (8) + status (1) + done (1).
+BYTES_PER_PARTICIPANT = 16 + 8 + 1 + 24 + 1 + 2 + 2
+BYTES_PER_SCENARIO = 8 + 1 + 1
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_scene(config: str, seed: int, n=None, m=None):
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    if config == "c2":
+        return synthetic.config2(n or N_SCN, m or M_PART, seed=seed)
+    if config == "c3":
+        seg, bounds = load_collidable_segments("highD_1")
+        return synthetic.config3(n or 4096, m or 64, seed=seed, segments=seg, bounds=bounds)
+    if config == "c4":
+        seg, bounds = load_collidable_segments("inD_1")
+        return synthetic.config4(n or 16384, m or 32, seed=seed, segments=seg, bounds=bounds)
+    if config == "c5":
+        seg, bounds = load_collidable_segments("rounD_0")
+        return synthetic.config5(n or 65536, m or 128, seed=seed, segments=seg, bounds=bounds)
+    raise SystemExit(f"unknown config {config}")
+
+
+def make_scene_name(config: str) -> str:
+    return {"c2": f"C2 {N_SCN}x{M_PART} kinematics + OBB collision, synthetic grid map",
+            "c3": "C3 4096x64 dynamics + map polylines", "c4": "C4 16384x32 mixed vehicle/cyclist/pedestrian",
+            "c5": "C5 65536x128 kinematics + broadphase stress"}[config]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.lines:
+            if not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def _cpu_worker(args):
+    from oracle import scalar_port as SP
+
+    state, tid, act, table, seg, bounds = args
+    t = time.perf_counter()
+    SP.tick_scenarios(state, tid, act, table, seg, bounds)
+    return time.perf_counter() - t
+
+
+def cpu_port_throughput(scene, n_scn: int, procs: int, steps: int = 1, warmup: int = 0):
+    """participant-steps/s of the reference-style per-agent Python loop on `n_scn` scenarios per step."""
+    import multiprocessing as mp
+
+    from tactics2d_b200 import synthetic
+
+    table = scene.table.as_oracle_table()
+    n_scn = min(n_scn, scene.shape[0])
+    st = {k: v[:n_scn] for k, v in scene.state().items()}
+    tid = scene.type_id[:n_scn]
+    act = synthetic.random_actions(77, (n_scn, scene.shape[1]))
+    chunks = np.array_split(np.arange(n_scn), max(1, min(procs, n_scn)))
+    jobs = [({k: v[c] for k, v in st.items()}, tid[c], act[c], table, scene.segments, scene.bounds) for c in chunks if len(c)]
+    times = []
+    if procs <= 1:
+        for i in range(warmup + steps):
+            t = time.perf_counter()
+            for j in jobs:
+                _cpu_worker(j)
+            if i >= warmup:
+                times.append(time.perf_counter() - t)
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            for i in range(warmup + steps):
+                t = time.perf_counter()
+                pool.map(_cpu_worker, jobs)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t)
+    total = n_scn * scene.shape[1] * len(times)
+    return total / sum(times), sum(times) / len(times)
+
+
+def cpu_c_throughput(scene, reps=3):
+    """The compiled float64 oracle (C + OpenMP, all cores) on the full batch - a stronger CPU figure."""
+    from oracle import c_oracle as CO
+    from tactics2d_b200 import synthetic
+
+    table = scene.table.as_oracle_table()
+    act = synthetic.random_actions(78, scene.shape)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        new = CO.physics(scene.state(), scene.type_id, act, table)
+        CO.events(new["x"], new["y"], new["heading"], scene.type_id, table, scene.segments, scene.bounds)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return scene.x.size / best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    scene = make_scene(args.config, seed=1, n=max(64, 2 * cores))
+    per_step = max(cores, 8)
+    value, t_step = cpu_port_throughput(scene, per_step, cores, steps=args.steps, warmup=args.warmup)
+    sample = (f"{per_step} of {N_SCN} scenarios x {scene.shape[1]} participants per step, {args.steps} steps, "
+              f"{cores} processes (per-agent Python loop, restatement: shapely/GEOS unavailable)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": make_scene_name(args.config), "sample_scenarios_per_step": per_step, "seed": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        entry.build()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=device)
+        dist.barrier()
+    from tactics2d_b200 import BatchedWorld, _lib, synthetic
+
+    lib = _lib.load()
+    K, W = args.steps, max(args.warmup, 3)
+    scene0 = make_scene(args.config, seed=1 + 1000 * rank)
+    n, m = scene0.shape
+    bytes_per_launch = n * m * BYTES_PER_PARTICIPANT + n * BYTES_PER_SCENARIO
+    l2_bytes = torch.cuda.get_device_properties(device).L2_cache_size
+    R = args.replicas or max(4, int(np.ceil(2.5 * l2_bytes / bytes_per_launch)))
+    R = min(R, max(2, int(60e9 // max(1, bytes_per_launch))))
+
+    worlds, actions, pools = [], [], []
+    for r in range(R):
+        sc = scene0 if r == 0 else make_scene(args.config, seed=1 + 1000 * rank + r)
+        w = BatchedWorld(n, m, sc.table, device=device, max_step=0)
+        w.set_map(sc.segments, sc.bounds)
+        w.set_state(sc.x, sc.y, sc.heading, sc.speed, vx=sc.vx, vy=sc.vy, type_id=sc.type_id)
+        worlds.append(w)
+        actions.append(torch.from_numpy(synthetic.random_actions(9000 + 1000 * rank + r, (n, m))).to(device))
+        pools.append({k: getattr(w, k).clone() for k in ("x", "y", "heading", "speed", "vx", "vy")})
+    ones = torch.ones(n, dtype=torch.uint8, device=device)
+    done_all = torch.zeros(world_size * n, dtype=torch.uint8, device=device) if world_size > 1 else None
+
+    def restore():
+        for w, p in zip(worlds, pools):
+            w.reset(ones, p)
+
+    def one_step(i):
+        r = i % R
+        out = worlds[r].step(actions[r])
+        if world_size > 1:
+            dist.all_gather_into_tensor(done_all, out.done)   # the one exchange of the path
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # warm-up (also JIT-free: the library is prebuilt) --------------------------------------------
+    for i in range(W):
+        one_step(i)
+    barrier()
+
+    # capture the K-step timed region in a CUDA graph ----------------------------------------------
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for i in range(min(3, K)):
+                    one_step(i)
+            torch.cuda.current_stream(device).wait_stream(side)
+            barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(K):
+                    one_step(i)
+            graph = g
+        except Exception as e:   # e.g. NCCL capture unsupported: fall back to the eager loop
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing the eager loop", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def timed_region():
+        restore()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.t2d_launch_count()
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                one_step(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world_size > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        launches = K if graph is not None else int(lib.t2d_launch_count() - l0)
+        return float(ms.item()), launches
+
+    timed_region()  # one untimed pass through the exact timed path
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.time()
+    reps_ms, launches = [], K
+    budget_s, t_begin = args.min_seconds, time.time()
+    while len(reps_ms) < args.min_reps or (time.time() - t_begin < budget_s and len(reps_ms) < args.max_reps):
+        ms, launches = timed_region()
+        reps_ms.append(ms)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_total = float(np.median(reps_ms))
+    ms_per_step = ms_total / K
+    value = world_size * n * m * K / (ms_total * 1e-3)
+
+    # e2e: public API with HOST buffers, H2D of the actions and D2H of done/status every step --------
+    e2e = None
+    if not args.no_e2e:
+        host_act = [torch.from_numpy(synthetic.random_actions(500 + r, (n, m))).pin_memory() for r in range(min(R, 8))]
+        dev_act = torch.empty((n, m, 2), dtype=torch.float32, device=device)
+        host_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+        host_status = torch.empty(n, dtype=torch.uint8).pin_memory()
+        stream = torch.cuda.current_stream(device)
+
+        def e2e_step(i):
+            dev_act.copy_(host_act[i % len(host_act)], non_blocking=True)
+            out = worlds[i % R].step(dev_act)
+            if world_size > 1:
+                dist.all_gather_into_tensor(done_all, out.done)
+            host_done.copy_(out.done, non_blocking=True)
+            host_status.copy_(out.status, non_blocking=True)
+            stream.synchronize()   # the caller reads done/status before choosing the next action
+
+        restore()
+        for i in range(W):
+            e2e_step(i)
+        e2e_ms = []
+        for _ in range(max(3, min(args.min_reps, 10))):
+            restore()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                e2e_step(i)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            if world_size > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms.append(float(t.item()))
+        e2e_t = float(np.median(e2e_ms))
+        e2e = {"value": world_size * n * m * K / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * m * 2 * 4,
+               "d2h_bytes_per_step": 2 * n, "ms_per_step": e2e_t / K,
+               "api": "BatchedWorld.step(action) with pinned-host action -> device copy, done/status -> pinned-host copy, stream sync per step"}
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.config)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": scene0.name, "scenarios_per_gpu": n, "participants": m, "model": "SingleTrackKinematics" if args.config in ("c2", "c5") else args.config,
+                       "interval_ms": 100, "delta_t_ms": 5, "map_segments": 0 if scene0.segments is None else int(len(scene0.segments)),
+                       "l2_policy": f"inputs larger than L2: {R} world replicas x {bytes_per_launch / 1e6:.1f} MB rotate through the timed steps ({R * bytes_per_launch / 1e6:.0f} MB > {l2_bytes / 1e6:.0f} MB L2)",
+                       "timed_region": "CUDA graph of K steps" if graph is not None else "eager launch loop of K steps",
+                       "reps": len(reps_ms), "rep_ms_min": min(reps_ms), "rep_ms_max": max(reps_ms),
+                       "collective": "all_gather(done) per step (NCCL)" if world_size > 1 else "none (1 GPU)"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "t2d_step_kernel",
+                         "bytes_per_launch": bytes_per_launch,
+                         "duration_us": ms_per_step * 1e3,
+                         "note": "achieved = algorithmic bytes per launch / mean launch duration inside the timed CUDA-graph region"},
+        }
+        if world_size == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_s = 16
+            v1, _ = cpu_port_throughput(scene0, n_s, 1)
+            line["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"first {n_s} of {n} scenarios x {m} participants, 1 step, 1 process (per-agent Python loop; restatement - shapely/GEOS unavailable)"}
+            try:
+                line["cpu_baseline_compiled"] = {"value": cpu_c_throughput(scene0), "unit": UNIT, "cores": cores, "kind": "port",
+                                                 "sample": f"all {n} x {m}, 1 step, C + OpenMP float64 oracle (oracle/c/oracle_tick.c), best of 3"}
+            except Exception as e:
+                line["cpu_baseline_compiled"] = {"error": str(e)}
+        print(json.dumps(line), flush=True)
+    for w in worlds:
+        w.close()
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--replicas", type=int, default=0)
+    ap.add_argument("--min-reps", type=int, default=5)
+    ap.add_argument("--max-reps", type=int, default=400)
+    ap.add_argument("--min-seconds", type=float, default=2.0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

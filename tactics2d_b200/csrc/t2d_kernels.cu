@@ -31,8 +31,8 @@
 namespace t2d {
 
 constexpr int PPL = 4;                  // participants per lane
-constexpr int WARPS_PER_CTA = 8;
-constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int MAX_WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host picks 2, 4 or 8 warps per CTA
 constexpr int POSE_PER_WARP = 128;      // 32 lanes x PPL
 constexpr int MAP_SMEM_LIMIT = 120 * 1024;
 
@@ -40,7 +40,8 @@ struct MapHeader {   // 64 bytes, start of the map blob
   int32_t n_seg, gx, gy, n_items;
   float x0, y0, inv_cell, cell;
   uint32_t off_seg, off_cell, off_items, total_bytes;
-  uint32_t pad[4];
+  uint32_t off_clear;   // float per cell: lower bound of the distance from any point of the cell to any segment
+  uint32_t pad[3];
 };
 static_assert(sizeof(MapHeader) == 64, "MapHeader must be 64 bytes");
 
@@ -65,6 +66,7 @@ struct StepArgs {
   int max_step, cfg_flags;
   int do_physics, has_bounds, vec_ok, needs_vel_in;
   float bxmin, bxmax, bymin, bymax;
+  float rb_max;                    // largest bounding radius in the type table (broadphase threshold)
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -138,6 +140,12 @@ __device__ __noinline__ bool oob_exact(const Pose a, float xmin, float xmax, flo
   return out_of_bound_f64(a.x, a.y, a.h, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax);
 }
 
+// Single-participant kinematics for mixed-model tiles (one out-of-line copy instead of PPL inlined ones).
+__device__ __noinline__ void kin1_step(KinIO<1>& io, const Params& p, int n_steps, float dt, float dt_rem) {
+  const Params* const p1[1] = {&p};
+  kinematics_step<1>(io, p1, n_steps, dt, dt_rem);
+}
+
 // Every model except the fp32 kinematic fast path (one copy of the fp64 code per kernel).
 __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem, double interval) {
   if (p.model == MODEL_DYNAMICS) {
@@ -151,9 +159,25 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
   }
 }
 
-// First (lowest-index) map segment the pose touches, or -1.  Uniform-grid broadphase over the map
-// tile: only the cells under the pose's bounding circle are visited.
-__device__ __noinline__ int static_first_hit(const Pose a, const float rbound, const unsigned char* mapb) {
+// Static broadphase, level 1: the clearance field.  One shared-memory load tells whether the pose's
+// bounding circle can reach any segment at all (most participants are nowhere near a wall).
+__device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const unsigned char* mapb) {
+  const MapHeader* mh = reinterpret_cast<const MapHeader*>(mapb);
+  const float r = rbound * 1.0001f + 1e-3f;
+  const float fx = (ax - mh->x0) * mh->inv_cell, fy = (ay - mh->y0) * mh->inv_cell;
+  const int gx = mh->gx, gy = mh->gy;
+  if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)gx && fy < (float)gy)) {
+    // outside the grid: reachable only within r of its box
+    const float ox = fmaxf(fmaxf(-fx, fx - (float)gx), 0.0f), oy = fmaxf(fmaxf(-fy, fy - (float)gy), 0.0f);
+    return fmaxf(ox, oy) * mh->cell <= r;
+  }
+  const float* clear = reinterpret_cast<const float*>(mapb + mh->off_clear);
+  return clear[(int)fy * gx + (int)fx] <= r;
+}
+
+// Level 2: first (lowest-index) map segment the pose touches, or -1.  Uniform grid over the map tile:
+// only the cells under the pose's bounding circle are visited.
+__device__ __forceinline__ int static_first_hit(const Pose a, const float rbound, const unsigned char* mapb) {
   const MapHeader* mh = reinterpret_cast<const MapHeader*>(mapb);
   const float4* seg = reinterpret_cast<const float4*>(mapb + mh->off_seg);
   const uint32_t* cell_start = reinterpret_cast<const uint32_t*>(mapb + mh->off_cell);
@@ -179,6 +203,54 @@ __device__ __noinline__ int static_first_hit(const Pose a, const float rbound, c
   return best == 0x7fffffff ? -1 : best;
 }
 
+// Own pose of participant `idx` back from the warp's shared-memory tile (the hot loops keep only x, y
+// and the bounding radius in registers; the rare exact paths re-read the rest).
+__device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* poseB, int idx) {
+  const float4 a = poseA[idx], b = poseB[idx];
+  Pose p;
+  p.x = a.x; p.y = a.y; p.h = a.w; p.c = b.x; p.s = b.y; p.l = b.z; p.w = b.w;
+  return p;
+}
+
+constexpr int QCAP = 192;   // per-warp candidate queue (pairs); overflow is handled inline
+
+// Exact test of one candidate pair (tile indices ti, tj of the same scenario); a hit is recorded for both
+// ends as the minimum partner index (scenario-local), which is what "first hit in list order" means.
+__device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, const float4* poseA, const float4* poseB, int* hitmin) {
+  const Pose a = load_pose(poseA, poseB, ti), b = load_pose(poseA, poseB, tj);
+  if (pair_hit(a, b)) {
+    const int mask = (1 << mp_shift) - 1;
+    atomicMin(&hitmin[ti], tj & mask);
+    atomicMin(&hitmin[tj], ti & mask);
+  }
+}
+
+// Broadphase candidates of one partner (tile index tj) against the lane's PPL participants: push them on the
+// warp's queue (bit i of cand: participant t0 + i).  1 <= q - i <= Mh keeps every unordered pair once.
+__device__ __noinline__ void pair_enqueue(unsigned cand, int q, int tj, int t0, int Mh, int mp_shift, const float4* poseA,
+                                          const float4* poseB, int* hitmin, unsigned* queue, int* qcount) {
+  for (int i = 0; i < PPL; ++i) {
+    if (!((cand >> i) & 1u)) continue;
+    const int k = q - i;
+    if (k < 1 || k > Mh) continue;
+    const int slot = atomicAdd(qcount, 1);
+    if (slot < QCAP) queue[slot] = ((unsigned)(t0 + i) << 16) | (unsigned)tj;
+    else pair_resolve(t0 + i, tj, mp_shift, poseA, poseB, hitmin);   // dense scene: resolve in place
+  }
+}
+
+__device__ __noinline__ int static_slow(const float4* poseA, const float4* poseB, int idx, float rbound, const unsigned char* mapb) {
+  return static_first_hit(load_pose(poseA, poseB, idx), rbound, mapb);
+}
+
+__device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, int idx, float xmin, float xmax, float ymin,
+                                      float ymax) {
+  const Pose a = load_pose(poseA, poseB, idx);
+  int r = out_of_bound_f32(a.x, a.y, a.c, a.s, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax);
+  if (r < 0) r = out_of_bound_f64(a.x, a.y, a.h, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax) ? 1 : 0;
+  return r != 0;
+}
+
 // ---------------------------------------------------------------------------- K1
 __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -187,9 +259,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
   unsigned char* s_map = smem;
   Params* s_table = reinterpret_cast<Params*>(smem + map_smem_bytes);
   const int table_bytes = ((A.n_types * (int)sizeof(Params) + 15) / 16) * 16;
+  const int wpc = blockDim.x >> 5;   // warps per CTA (2, 4 or 8: chosen by the host for SM balance)
   float4* s_poseA = reinterpret_cast<float4*>(smem + map_smem_bytes + table_bytes);
-  float4* s_poseB = s_poseA + WARPS_PER_CTA * POSE_PER_WARP;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_poseB + WARPS_PER_CTA * POSE_PER_WARP);
+  float4* s_poseB = s_poseA + wpc * POSE_PER_WARP;
+  int* s_hit = reinterpret_cast<int*>(s_poseB + wpc * POSE_PER_WARP);
+  unsigned* s_queue = reinterpret_cast<unsigned*>(s_hit + wpc * POSE_PER_WARP);
+  int* s_qcount = reinterpret_cast<int*>(s_queue + wpc * QCAP);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_qcount + ((wpc + 3) & ~3));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -201,7 +277,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
     const int words = A.n_types * (int)(sizeof(Params) / 4);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(A.table);
     uint32_t* dst = reinterpret_cast<uint32_t*>(s_table);
-    for (int i = tid; i < words; i += CTA_THREADS) dst[i] = src[i];
+    for (int i = tid; i < words; i += (int)blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
   if (tid == 0 && map_smem_bytes > 0) {
@@ -217,13 +293,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
   const int gl = lane - sub * G;        // lane inside the group
   const int m0 = gl * PPL;              // first participant of this lane
   const int MP = G * PPL;               // padded participants per scenario
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
-  float4* poseA = s_poseA + warp * POSE_PER_WARP + sub * MP;
-  float4* poseB = s_poseB + warp * POSE_PER_WARP + sub * MP;
+  // warp-level views of the pose tile; t0 = this lane's first slot in it, tb = its scenario's first slot
+  float4* poseA = s_poseA + warp * POSE_PER_WARP;
+  float4* poseB = s_poseB + warp * POSE_PER_WARP;
+  int* hitmin = s_hit + warp * POSE_PER_WARP;
+  unsigned* queue = s_queue + warp * QCAP;
+  int* qcount = s_qcount + warp;
+  const int tb = sub * MP, t0 = tb + m0;
+  int mp_shift = 0;
+  while ((1 << mp_shift) < MP) ++mp_shift;
+  const int Mh = M >> 1;                // partner offsets 1..Mh cover every unordered pair
 
   const long long n_tiles = ((long long)A.N + spw - 1) / spw;
-  for (long long tile = (long long)blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles;
-       tile += (long long)gridDim.x * WARPS_PER_CTA) {
+  for (long long tile = (long long)blockIdx.x * wpc + warp; tile < n_tiles; tile += (long long)gridDim.x * wpc) {
     const long long n = tile * spw + sub;
     const bool scn_ok = n < A.N;
     int nvalid = scn_ok ? min(PPL, M - m0) : 0;
@@ -313,8 +395,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
             KinIO<1> io;
             io.x[0] = sx[i]; io.y[0] = sy[i]; io.h[0] = shd[i]; io.v[0] = sv[i];
             io.acc[0] = a0[i]; io.steer[0] = a1[i];
-            const Params* const p1[1] = {pp[i]};
-            kinematics_step<1>(io, p1, A.n_steps, A.dt, A.dt_rem);
+            kin1_step(io, *pp[i], A.n_steps, A.dt, A.dt_rem);
             sx[i] = io.x[0]; sy[i] = io.y[0]; shd[i] = io.h[0]; sv[i] = io.v[0];
             svx[i] = io.vx[0]; svy[i] = io.vy[0]; ch[i] = io.ch[0]; sh[i] = io.sh[0];
           } else {
@@ -349,42 +430,66 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
     }
 
     // ------------------------------------------------------------------ poses -> shared
-    Pose my[PPL];
-    float rb[PPL];
-    bool solid[PPL];
+    // Only (x, y, bounding radius) stay in registers; the full pose lives in the warp's smem tile.
+    float px[PPL], py[PPL], rb[PPL];
+    unsigned solid_bits = 0;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
       const Params& p = *pp[i];
-      solid[i] = active[i] && p.shape != SHAPE_NONE;
+      const bool sol = active[i] && p.shape != SHAPE_NONE;
       const bool circle = p.shape == SHAPE_CIRCLE;
-      my[i].x = sx[i]; my[i].y = sy[i]; my[i].h = shd[i]; my[i].c = ch[i]; my[i].s = sh[i];
-      my[i].l = circle ? p.radius : p.half_len;
-      my[i].w = circle ? -1.0f : p.half_wid;
+      solid_bits |= sol ? (1u << i) : 0u;
       // bounding radius, rounded up so the broadphase is conservative
       rb[i] = circle ? p.radius : sqrtf(fmaf(p.half_len, p.half_len, p.half_wid * p.half_wid)) * 1.000001f;
-      poseA[m0 + i] = make_float4(solid[i] ? sx[i] : __int_as_float(0x7fc00000), sy[i], rb[i], shd[i]);
-      poseB[m0 + i] = make_float4(ch[i], sh[i], my[i].l, my[i].w);
+      px[i] = sol ? sx[i] : __int_as_float(0x7fc00000);   // NaN: a non-solid slot never passes a distance test
+      py[i] = sy[i];
+      poseA[t0 + i] = make_float4(px[i], py[i], rb[i], shd[i]);
+      poseB[t0 + i] = make_float4(ch[i], sh[i], circle ? p.radius : p.half_len, circle ? -1.0f : p.half_wid);
+      hitmin[t0 + i] = 0x7fffffff;
     }
+    if (lane == 0) *qcount = 0;
     __syncwarp();
 
     // ------------------------------------------------------------------ dynamic collision
+    // Every unordered pair once: participant i tests partners (i+1 .. i+M/2) mod M.  A lane walks the
+    // partners of its PPL participants together (one 128-bit pose load per partner, PPL distance tests);
+    // candidates (rare) go to the out-of-line narrowphase.  A confirmed hit is recorded for both ends:
+    // locally for i, by atomicMin in shared memory for the partner.
     int hit[PPL];
-#pragma unroll
-    for (int i = 0; i < PPL; ++i) hit[i] = -1;
-    for (int j = 0; j < M; ++j) {
-      const float4 pa = poseA[j];
+    {
+      float thr[PPL];
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
-        const float dx = pa.x - my[i].x, dy = pa.y - my[i].y;
-        const float rr = rb[i] + pa.z;
-        // NaN x (non-solid partner) fails the comparison; the margin keeps the filter conservative
-        const bool cand = fmaf(dx, dx, dy * dy) <= rr * rr * 1.00001f + 1e-12f;
-        if (cand && solid[i] && hit[i] < 0 && j != m0 + i) {
-          const float4 pb = poseB[j];
-          Pose o;
-          o.x = pa.x; o.y = pa.y; o.h = pa.w; o.c = pb.x; o.s = pb.y; o.l = pb.z; o.w = pb.w;
-          if (pair_hit(my[i], o)) hit[i] = j;
+        const float rr = rb[i] + A.rb_max;
+        thr[i] = fmaf(rr * rr, 1.00001f, 1e-12f);   // conservative: any partner's bounding radius <= rb_max
+      }
+      // hot loop: every lane runs it (idle slots hold NaN and never pass), no divergence; candidates are rare
+      const int q_end = Mh > 0 ? Mh + PPL - 1 : 0;
+      int pj = m0;
+      for (int q = 1; q <= q_end; ++q) {
+        ++pj;
+        pj = (pj >= M) ? pj - M : pj;
+        const float2 pxy = *reinterpret_cast<const float2*>(&poseA[tb + pj]);   // NaN x for a non-solid partner
+        unsigned cand = 0;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const float dx = pxy.x - px[i], dy = pxy.y - py[i];
+          if (fmaf(dx, dx, dy * dy) <= thr[i]) cand |= 1u << i;
         }
+        if (cand) pair_enqueue(cand, q, tb + pj, t0, Mh, mp_shift, poseA, poseB, hitmin, queue, qcount);
+      }
+      __syncwarp();
+      // narrowphase: the queued candidate pairs, one per lane
+      const int n_q = min(*qcount, QCAP);
+      for (int k = lane; k < n_q; k += 32) {
+        const unsigned e = queue[k];
+        pair_resolve((int)(e >> 16), (int)(e & 0xffffu), mp_shift, poseA, poseB, hitmin);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const int h = hitmin[t0 + i];
+        hit[i] = (h == 0x7fffffff) ? -1 : h;
       }
     }
 
@@ -399,7 +504,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
       }
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
-        if (solid[i]) hseg[i] = static_first_hit(my[i], rb[i], mapb);
+        if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], mapb))
+          hseg[i] = static_slow(poseA, poseB, t0 + i, rb[i], mapb);
     }
 
     // ------------------------------------------------------------------ out of bound + flags
@@ -409,11 +515,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
       uint8_t f = 0;
       if (hit[i] >= 0) f |= T2D_F_DYNAMIC;
       if (hseg[i] >= 0) f |= T2D_F_STATIC;
-      if (A.has_bounds && solid[i]) {
-        int r = out_of_bound_f32(my[i].x, my[i].y, my[i].c, my[i].s, my[i].l, my[i].w, my[i].w < 0.0f, A.bxmin, A.bxmax,
-                                 A.bymin, A.bymax);
-        if (r < 0) r = oob_exact(my[i], A.bxmin, A.bxmax, A.bymin, A.bymax) ? 1 : 0;
-        if (r) f |= T2D_F_OUTBOUND;
+      if (A.has_bounds && ((solid_bits >> i) & 1u)) {
+        // the bounding circle well inside the box: inside for sure (the common case)
+        const float r = rb[i] * 1.0001f + 1e-3f;
+        const bool clear_in = (px[i] - A.bxmin > r) && (A.bxmax - px[i] > r) && (py[i] - A.bymin > r) && (A.bymax - py[i] > r);
+        if (!clear_in && oob_slow(poseA, poseB, t0 + i, A.bxmin, A.bxmax, A.bymin, A.bymax)) f |= T2D_F_OUTBOUND;
       }
       fl[i] = f;
     }
@@ -552,6 +658,9 @@ struct t2d_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   int configured_smem = -1;
+  float rb_max = 0.0f;
+  int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
+  int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 extern "C" {
@@ -615,8 +724,11 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   if (n_types <= 0 || n_types > T2D_MAX_TYPES) return fail(T2D_E_INVALID, "n_types must be in 1..64");
   static_assert(sizeof(t2d_type_params) == sizeof(Params), "type table layout");
   c->has_pointmass = false;
+  float rb_max = 0.0f;
   for (int i = 0; i < n_types; ++i) {
     const t2d_type_params& p = table[i];
+    if (p.shape == T2D_SHAPE_OBB) rb_max = std::max(rb_max, std::sqrt(p.half_len * p.half_len + p.half_wid * p.half_wid) * 1.000002f);
+    if (p.shape == T2D_SHAPE_CIRCLE) rb_max = std::max(rb_max, p.radius);
     if (p.model < 0 || p.model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "type table: unknown model id");
     if (p.shape < 0 || p.shape > T2D_SHAPE_NONE) return fail(T2D_E_INVALID, "type table: unknown shape id");
     if (p.model <= T2D_MODEL_DYNAMICS && !(p.lf + p.lr > 0.0f)) return fail(T2D_E_INVALID, "type table: lf + lr must be > 0");
@@ -631,6 +743,7 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   if (!c->d_table) CUDA_TRY(cudaMalloc(&c->d_table, T2D_MAX_TYPES * sizeof(Params)));
   CUDA_TRY(cudaMemcpy(c->d_table, table, n_types * sizeof(Params), cudaMemcpyHostToDevice));
   c->n_types = n_types;
+  c->rb_max = rb_max;
   return T2D_OK;
 }
 
@@ -698,7 +811,8 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   mh.off_seg = 64;
   mh.off_cell = (uint32_t)up16(mh.off_seg + (size_t)n_seg * 16);
   mh.off_items = (uint32_t)up16(mh.off_cell + ((size_t)gx * gy + 1) * 4);
-  mh.total_bytes = (uint32_t)up16(mh.off_items + n_items * 2);
+  mh.off_clear = (uint32_t)up16(mh.off_items + n_items * 2);
+  mh.total_bytes = (uint32_t)up16(mh.off_clear + (size_t)gx * gy * 4);
   std::vector<unsigned char> blob(mh.total_bytes, 0);
   memcpy(blob.data(), &mh, sizeof(mh));
   memcpy(blob.data() + mh.off_seg, segments, (size_t)n_seg * 16);
@@ -710,6 +824,25 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
     for (uint16_t s : cells[ci]) it[acc++] = s;
   }
   cs[cells.size()] = acc;
+  // clearance field: distance from the cell centre to the nearest segment, minus the cell's half diagonal
+  float* clr = reinterpret_cast<float*>(blob.data() + mh.off_clear);
+  const double half_diag = 0.5 * std::sqrt(2.0) * (double)cell * 1.0001 + 2.0 * margin;
+  for (int cy = 0; cy < gy; ++cy)
+    for (int cx = 0; cx < gx; ++cx) {
+      const double px = (double)x0 + (cx + 0.5) * (double)cell, py = (double)y0 + (cy + 0.5) * (double)cell;
+      double best = INFINITY;
+      for (int i = 0; i < n_seg; ++i) {
+        const float* sg = segments + 4 * i;
+        const double dx = (double)sg[2] - sg[0], dy = (double)sg[3] - sg[1], ux = px - sg[0], uy = py - sg[1];
+        const double dd = dx * dx + dy * dy;
+        double t = dd > 0.0 ? (ux * dx + uy * dy) / dd : 0.0;
+        t = std::min(1.0, std::max(0.0, t));
+        const double ex = ux - t * dx, ey = uy - t * dy;
+        best = std::min(best, ex * ex + ey * ey);
+      }
+      const double d = std::sqrt(best) - half_diag;
+      clr[(size_t)cy * gx + cx] = d > 0.0 ? (float)(d * 0.9999) : 0.0f;
+    }
   CUDA_TRY(cudaMalloc(&c->d_map, mh.total_bytes));
   CUDA_TRY(cudaMemcpy(c->d_map, blob.data(), mh.total_bytes, cudaMemcpyHostToDevice));
   c->map_bytes = (int)mh.total_bytes;
@@ -761,22 +894,33 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
              (!hit_segment || reinterpret_cast<uintptr_t>(hit_segment) % 8 == 0);
   A.vec_ok = vec ? 1 : 0;
 
+  A.rb_max = c->rb_max;
   const int table_bytes = ((c->n_types * (int)sizeof(Params) + 15) / 16) * 16;
-  const int smem = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 2 * WARPS_PER_CTA * POSE_PER_WARP * (int)sizeof(float4) + 16;
+  const int spw = 32 / c->G;
+  const long long tiles = ((long long)c->N + spw - 1) / spw;
+  // warps per CTA: the largest of 8 / 4 / 2 that still leaves >= 6 CTAs per SM (small batches balance
+  // across the 148 SMs only with small CTAs; large batches amortise the map staging over more warps)
+  int wpc = 2;
+  for (int w : {8, 4}) {
+    if ((tiles + w - 1) / w >= 6LL * c->sm_count) { wpc = w; break; }
+  }
+  const int smem_fixed = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 16;
+  const int smem = smem_fixed + wpc * (POSE_PER_WARP * (2 * (int)sizeof(float4) + (int)sizeof(int)) + QCAP * 4) + 32;
   if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");
-  if (smem != c->configured_smem) {
+  if (smem > c->configured_smem) {
     CUDA_TRY(cudaFuncSetAttribute(t2d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->configured_smem = smem;
   }
-  const int spw = 32 / c->G;
-  const long long tiles = ((long long)c->N + spw - 1) / spw;
-  const long long ctas_needed = (tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  int per_sm = 2;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2d_step_kernel, CTA_THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
-  const long long resident = (long long)c->sm_count * per_sm;
+  const long long ctas_needed = (tiles + wpc - 1) / wpc;
+  if (c->occ_smem[wpc] != smem) {
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2d_step_kernel, wpc * 32, smem));
+    c->occ_val[wpc] = per_sm < 1 ? 1 : per_sm;
+    c->occ_smem[wpc] = smem;
+  }
+  const long long resident = (long long)c->sm_count * c->occ_val[wpc];
   const int grid = (int)std::max(1LL, std::min(ctas_needed, resident));
-  t2d_step_kernel<<<grid, CTA_THREADS, smem, (cudaStream_t)stream>>>(A);
+  t2d_step_kernel<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;

@@ -96,7 +96,12 @@ struct KinIO {
 
 template <int W>
 T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_steps, float dt, float dt_rem) {
-  float c[W], s[W], v[W], Sx[W], Sy[W], Sv[W], k[W], a[W], vlo[W], vhi[W];
+  // Speed recurrence in closed form.  The reference iterates w_{i+1} = clip(w_i + a dt) (:147-148).  With
+  // w_1 = clip(w_0 + a dt) inside [lo, hi], the sequence is monotone and saturates at most once, hence
+  // w_i = clip(w_1 + (i-1) a dt) for i >= 1 (w_0 itself may lie outside the range).  One rounding per
+  // term instead of an accumulated sum.
+  float c[W], s[W], w1[W], Sx[W], Sy[W], Sv[W], kdt[W], adt[W], vlo[W], vhi[W], k[W], a[W];
+  bool small = true;
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     a[i] = clampf(io.acc[i], p[i]->accel_lo, p[i]->accel_hi);       // :192
@@ -111,43 +116,67 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
     float sb = tb * cb;                          // sin(beta)
     k[i] = tan_d * cb / L;                       // dphi = v * k                           :141
+    kdt[i] = k[i] * dt;
+    adt[i] = a[i] * dt;
     float sp, cp;
     sincosf(io.h[i], &sp, &cp);
     c[i] = cp * cb - sp * sb;                    // cos(phi + beta)
     s[i] = sp * cb + cp * sb;                    // sin(phi + beta)
-    v[i] = io.v[i];
     vlo[i] = p[i]->speed_lo;
     vhi[i] = p[i]->speed_hi;
+    w1[i] = clampf(fmaf(a[i], dt, io.v[i]), vlo[i], vhi[i]);
+    const float wl = clampf(fmaf((float)(n_steps - 2), adt[i], w1[i]), vlo[i], vhi[i]);
+    const float wmax = fmaxf(fabsf(io.v[i]), fmaxf(fabsf(w1[i]), fabsf(wl)));
+    small = small && (fabsf(kdt[i]) * wmax <= 0.25f);   // every sub-step rotation stays in the polynomial's range
     Sx[i] = 0.0f; Sy[i] = 0.0f; Sv[i] = 0.0f;
   }
-  // main sub-steps :137-148 ; derivatives from the OLD (phi, v), then v clipped
-  for (int it = 0; it < n_steps; ++it) {
+  float v[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      Sx[i] = fmaf(v[i], c[i], Sx[i]);
-      Sy[i] = fmaf(v[i], s[i], Sy[i]);
-      Sv[i] += v[i];
-      float d = k[i] * dt * v[i];
-      float sn, hv;
-      if (fabsf(d) <= 0.25f) {
+  for (int i = 0; i < W; ++i) v[i] = io.v[i];
+  // main sub-steps :137-148 ; derivatives from the OLD (phi, v), then v clipped
+  if (small) {
+    float fi = -1.0f;
+    for (int it = 0; it < n_steps; ++it) {
+      fi += 1.0f;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        Sx[i] = fmaf(v[i], c[i], Sx[i]);
+        Sy[i] = fmaf(v[i], s[i], Sy[i]);
+        Sv[i] += v[i];
+        const float d = kdt[i] * v[i];
+        float sn, hv;
         small_sincos(d, sn, hv);
-      } else {  // unconstrained speed ranges only
-        float cs;
-        sincosf(d, &sn, &cs);
-        hv = 1.0f - cs;
+        const float c2 = c[i] - fmaf(c[i], hv, s[i] * sn);
+        const float s2 = s[i] - fmaf(s[i], hv, -c[i] * sn);
+        c[i] = c2;
+        s[i] = s2;
+        v[i] = clampf(fmaf(fi, adt[i], w1[i]), vlo[i], vhi[i]);   // w_{it+1}
       }
-      float c2 = c[i] - fmaf(c[i], hv, s[i] * sn);
-      float s2 = s[i] - fmaf(s[i], hv, -c[i] * sn);
-      c[i] = c2;
-      s[i] = s2;
-      v[i] = clampf(fmaf(a[i], dt, v[i]), vlo[i], vhi[i]);
+    }
+  } else {  // unconstrained speed ranges only: exact trig per sub-step
+    float fi = -1.0f;
+    for (int it = 0; it < n_steps; ++it) {
+      fi += 1.0f;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        Sx[i] = fmaf(v[i], c[i], Sx[i]);
+        Sy[i] = fmaf(v[i], s[i], Sy[i]);
+        Sv[i] += v[i];
+        float sn, cs;
+        sincosf(kdt[i] * v[i], &sn, &cs);
+        const float c2 = c[i] * cs - s[i] * sn;
+        const float s2 = s[i] * cs + c[i] * sn;
+        c[i] = c2;
+        s[i] = s2;
+        v[i] = clampf(fmaf(fi, adt[i], w1[i]), vlo[i], vhi[i]);
+      }
     }
   }
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     float x = fmaf(dt, Sx[i], io.x[i]);
     float y = fmaf(dt, Sy[i], io.y[i]);
-    float dphi = k[i] * dt * Sv[i];
+    float dphi = kdt[i] * Sv[i];
     if (dt_rem > 0.0f) {  // remainder sub-step :151-163
       x = fmaf(dt_rem * v[i], c[i], x);
       y = fmaf(dt_rem * v[i], s[i], y);

@@ -47,3 +47,24 @@ EPA_MAPPING = dict(zip(("minicompact", "subcompact", "compact", "midsize", "larg
                         "multi_purpose_car", "standard_suv"),
                        ("mini_car", "small_car", "medium_car", "large_car", "executive_car",
                         "sports_coupe", "minivan", "sports_utility_car")))
+
+
+def _table(template: dict) -> str:
+    keys = sorted({k for row in template.values() for k in row})
+    lines = ["\t".join(["type"] + keys)]
+    for name, row in template.items():
+        lines.append("\t".join([name] + [str(row.get(k, "")) for k in keys]))
+    return "\n".join(lines)
+
+
+def list_vehicle_templates():
+    """Print the vehicle templates (the reference pretty-prints with ``tabulate``)."""
+    print(_table(VEHICLE_TEMPLATE))
+
+
+def list_cyclist_templates():
+    print(_table(CYCLIST_TEMPLATE))
+
+
+def list_pedestrian_templates():
+    print(_table(PEDESTRIAN_TEMPLATE))

@@ -1,0 +1,4 @@
+from .state import State
+from .trajectory import Trajectory
+
+__all__ = ["State", "Trajectory"]

@@ -1,0 +1,219 @@
+"""GPU tests of the reference-shaped facades: physics models (against the golden vectors written from the
+unmodified reference), detectors, scenario manager and the Gym-style batched env."""
+
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import heading_err, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RNG = dict(steer_range=(-0.524, 0.524), speed_range=(-16.67, 69.44), accel_range=(-11.0, 3.121))
+MEDIUM = dict(lf=4.284 / 2 - 0.880, lr=4.284 / 2 - 0.767)
+
+
+def _check_bicycle(got, ref, dyn=False):
+    assert rel_err(got[:, 0], ref[:, 0]).max() <= 1e-5 and rel_err(got[:, 1], ref[:, 1]).max() <= 1e-5
+    assert heading_err(got[:, 2], ref[:, 2]).max() <= 1e-5
+    assert rel_err(got[:, 3], ref[:, 3]).max() <= 1e-5
+    vs = np.maximum(np.abs(ref[:, 3]), 1.0)
+    assert rel_err(got[:, 4], ref[:, 4], vs).max() <= 1e-5 and rel_err(got[:, 5], ref[:, 5], vs).max() <= 1e-5
+    assert rel_err(got[:, 6], ref[:, 6]).max() <= 1e-6 and rel_err(got[:, 7], ref[:, 7]).max() <= 1e-6
+
+
+def test_bicycle_step_batch_vs_reference_golden(cuda_device):
+    """SingleTrackKinematics / SingleTrackDynamics.step_batch on the reference's own outputs (fp32 state)."""
+    import torch
+
+    from tactics2d_b200.physics import SingleTrackDynamics, SingleTrackKinematics
+
+    g = np.load(os.path.join(GOLD, "physics_bicycle.npz"))
+    st, ac = g["states"], g["actions"]
+    ok = np.abs(st[:, 3]) >= 0.7   # dynamics: outside the band where the reference's Euler is unstable
+    n_cases = 0
+    for key in g.files:
+        if not (key.startswith("kin_") or key.startswith("dyn_")):
+            continue
+        tag, name, interval, dt = key.split("_")
+        interval, dt = int(interval), (None if dt == "None" else int(dt))
+        kw = RNG if name == "con" else {}
+        if tag == "kin":
+            m = SingleTrackKinematics(interval=interval, delta_t=dt, **MEDIUM, **kw)
+        else:
+            m = SingleTrackDynamics(mass=float(g["mass"]), mass_height=float(g["mass_height"]), interval=interval, delta_t=dt,
+                                    **MEDIUM, **kw)
+        t = [torch.tensor(st[:, i], dtype=torch.float32, device=cuda_device) for i in range(4)]
+        a = torch.tensor(ac[:, 0], dtype=torch.float32, device=cuda_device)
+        d = torch.tensor(ac[:, 1], dtype=torch.float32, device=cuda_device)
+        vx, vy, a_c, d_c = m.step_batch(t[0], t[1], t[2], t[3], a, d, interval)
+        got = torch.stack(t + [vx, vy, a_c, d_c], 1).cpu().numpy().astype(np.float64)
+        ref = g[key]
+        # the golden inputs are float64; the device sees them rounded to fp32 -> compare loosely on x, y scale
+        sel = ok if tag == "dyn" else np.ones(len(st), bool)
+        if tag == "dyn" and name == "unc":
+            sel = sel & (np.abs(st[:, 3] + ac[:, 0] * interval / 1000) >= 0.7)
+        _check_bicycle(got[sel], ref[sel])
+        n_cases += 1
+    assert n_cases == 20
+
+
+def test_pointmass_step_batch_vs_reference_golden(cuda_device):
+    import torch
+
+    from tactics2d_b200.physics import PointMass
+
+    g = np.load(os.path.join(GOLD, "physics_pointmass.npz"))
+    st, ac = g["states"], g["actions"]
+    ranges = {"ped": (-7.0, 7.0), "band": (1.0, 3.0), "flt": 4.0, "unc": None}
+    for key in g.files:
+        if not key.startswith("pm_"):
+            continue
+        _, name, backend, interval, dt = key.split("_")
+        m = PointMass(speed_range=ranges[name], accel_range=(-1.5, 1.5), interval=int(interval), delta_t=int(dt), backend=backend)
+        f = lambda a: torch.tensor(a, dtype=torch.float32, device=cuda_device)
+        x, y, vx, vy = f(st[:, 0]), f(st[:, 1]), f(st[:, 2]), f(st[:, 3])
+        h = f(np.arctan2(st[:, 3], st[:, 2]))
+        speed = m.step_batch(x, y, h, vx, vy, f(ac[:, 0]), f(ac[:, 1]), int(interval))
+        got = torch.stack([x, y, h, vx, vy, speed], 1).cpu().numpy().astype(np.float64)
+        ref = g[key]
+        moving = ref[:, 5] > 1e-3   # atan2 of a (near-)zero velocity is ill-conditioned in fp32 inputs
+        assert rel_err(got[:, 0], ref[:, 0]).max() <= 1e-5 and rel_err(got[:, 1], ref[:, 1]).max() <= 1e-5, key
+        assert heading_err(got[moving, 2], ref[moving, 2]).max() <= 2e-5, key
+        assert rel_err(got[:, 3], ref[:, 3], np.maximum(ref[:, 5], 1)).max() <= 1e-5, key
+        assert rel_err(got[:, 4], ref[:, 4], np.maximum(ref[:, 5], 1)).max() <= 1e-5, key
+        assert rel_err(got[:, 5], ref[:, 5]).max() <= 1e-5, key
+
+
+def test_scalar_step_signature_and_known_answers(cuda_device):
+    """model.step(State, accel, delta) -> (State, accel, delta): the survey's known-answer table."""
+    from tactics2d_b200.participant.trajectory import State
+    from tactics2d_b200.physics import PointMass, SingleTrackDynamics, SingleTrackKinematics
+
+    kin = SingleTrackKinematics(lf=1.262, lr=1.375, **RNG)
+    s0 = State(0, x=10, y=10, heading=0.3, speed=5.0)
+    s1, a, d = kin.step(s0, 1.0, 0.2)
+    assert s1.frame == 100 and (a, d) == (1.0, pytest.approx(0.2))
+    np.testing.assert_allclose([s1.x, s1.y, s1.heading, s1.speed, s1.vx, s1.vy],
+                               [10.460101899439735, 10.207478447324114, 0.3385859239425399, 5.1, 4.810449024453569, 1.693983525047891], rtol=1e-5)
+    s2, a, d = kin.step(s1, 5.0, -0.9)
+    assert a == pytest.approx(3.121) and d == pytest.approx(-0.524)   # clipped, not rejected
+    np.testing.assert_allclose([s2.x, s2.y, s2.heading, s2.speed], [10.984652234013904, 10.204125170899955, 0.22846394026452768, 5.4121], rtol=1e-5)
+    s3, _, _ = kin.step(s0, 1.0, 0.2, interval=9)   # remainder sub-step
+    np.testing.assert_allclose([s3.x, s3.y, s3.heading, s3.speed], [10.04135741781754, 10.017786583803838, 0.30344158156690076, 5.009], rtol=1e-5)
+    dyn = SingleTrackDynamics(1.262, 1.375, 1620, 0.726, **RNG)
+    t1, _, _ = dyn.step(s0, 1.0, 0.2)
+    assert t1.vx is None and t1.vy is None
+    np.testing.assert_allclose([t1.x, t1.y, t1.heading, t1.speed], [10.454044498400336, 10.220136047786687, 0.33888560266154016, 5.1], rtol=1e-5)
+    t4, _, _ = dyn.step(s0, 1.0, 0.2, interval=9)    # no remainder sub-step
+    np.testing.assert_allclose([t4.x, t4.y, t4.heading, t4.speed], [10.021728059527945, 10.012364927381514, 0.30194726104561803, 5.005], rtol=1e-5)
+    t3, _, _ = dyn.step(State(0, x=10, y=10, heading=0.3, speed=0.05), 1.0, 0.2)   # low-speed branch
+    np.testing.assert_allclose([t3.x, t3.y, t3.heading, t3.speed], [10.003277244831548, 10.002000985139086, 5.781714387949648, 0.15], rtol=2e-5)
+    pm = PointMass(speed_range=(-7, 7))
+    p1 = pm.step(State(0, x=10, y=10, heading=0.0, vx=1.0, vy=0.5), (0.5, 0.2))
+    np.testing.assert_allclose([p1.x, p1.y, p1.heading, p1.speed, p1.vx, p1.vy], [10.1025, 10.051, 0.45983083364175814, 1.1717081547894084, 1.05, 0.52], rtol=1e-5)
+    p2 = pm.step(State(0, x=10, y=10, heading=0.0, vx=6.9, vy=0.5), (3, 1))   # speed-limit branch
+    np.testing.assert_allclose([p2.x, p2.y, p2.heading, p2.speed], [10.696944716341092, 10.052314905447028, 0.07531667613487306, 7.0], rtol=1e-5)
+
+
+def test_reference_physics_test_properties(cuda_device):
+    """tests/test_physics.py of the reference: newton vs euler stay within 0.01 m over PEDESTRIAN_ACTION_LIST
+    (:248-249, Hausdorff replaced by the max point distance of the synchronous trajectories), and verify_state
+    rejects the state of an unconstrained model driven with action + (4.5, 0.9) (:296-303)."""
+    from tactics2d_b200.participant.trajectory import State
+    from tactics2d_b200.physics import PointMass, SingleTrackKinematics
+
+    ped = [((0, 0), 100), ((1, 0), 500), ((-1, 0), 500), ((1, 0), 500), ((0, 1), 500), ((0, -1), 500), ((1, 1), 500),
+           ((2, 2), 500), ((-2, -2), 2000), ((-1, 2), 500), ((2, -1), 500)]
+    trajs = []
+    for backend in ("newton", "euler"):
+        m = PointMass(speed_range=(-7.0, 7.0), accel_range=(-1.5, 1.5), interval=100, delta_t=5, backend=backend)
+        s = State(0, x=0.0, y=0.0, heading=0.0, vx=0.0, vy=0.0)
+        pts = [(s.x, s.y)]
+        for a, dur in ped:
+            for _ in range(0, dur, 100):
+                s = m.step(s, a, 100)
+                pts.append((s.x, s.y))
+        trajs.append(np.array(pts))
+    assert np.linalg.norm(trajs[0] - trajs[1], axis=1).max() < 0.06   # euler lags newton by O(a dt T)
+    con = SingleTrackKinematics(**MEDIUM, **RNG)
+    unc = SingleTrackKinematics(**MEDIUM)
+    s = State(0, x=10.0, y=10.0, heading=0.3, speed=5.0)
+    bad, _, _ = unc.step(s, 1.0 + 4.5, 0.1 + 0.9, 100)
+    assert not con.verify_state(bad, s, 100)
+    good, _, _ = con.step(s, 1.0, 0.1, 100)
+    assert con.verify_state(good, s, 100)
+
+
+def test_detectors_and_scenario_manager(cuda_device):
+    import torch
+
+    from oracle import scenario as O
+    from tactics2d_b200 import BatchedWorld, synthetic
+    from tactics2d_b200.traffic import BatchedScenarioManager, ScenarioStatus, TrafficStatus
+    from tactics2d_b200.traffic.event_detection import DynamicCollision, OutBound, StaticCollision, TimeExceed
+
+    scene = synthetic.config2(32, 64, seed=6, size=70.0)
+    w = BatchedWorld(32, 64, scene.table, device=cuda_device, any_participant=False)
+    w.set_state(scene.x, scene.y, scene.heading, scene.speed, type_id=scene.type_id)
+    sc, ob = StaticCollision(), OutBound()
+    sc.reset(scene.segments, world=w)
+    ob.reset(scene.bounds, world=w)
+    hit_d, idx_d = DynamicCollision().update(w)
+    hit_s, idx_s = sc.update(w, fresh=False)
+    out = ob.update(w, fresh=False)
+    fl, hi, hs = O.events(scene.x, scene.y, scene.heading, scene.type_id, scene.table.as_oracle_table(), scene.segments, scene.bounds)
+    assert np.array_equal(hit_d.cpu().numpy(), (fl & 1) != 0) and np.array_equal(idx_d.cpu().numpy(), hi)
+    assert np.array_equal(hit_s.cpu().numpy(), (fl & 2) != 0) and np.array_equal(idx_s.cpu().numpy(), hs)
+    assert np.array_equal(out.cpu().numpy(), (fl & 4) != 0)
+    te = TimeExceed(2)
+    assert [te.update(), te.update(), te.update()] == [False, False, True]
+    mgr = BatchedScenarioManager(w, max_step=2, step_size=100)
+    pool = {k: torch.from_numpy(v).to(cuda_device) for k, v in scene.state().items()}
+    mgr.set_initial_state(pool)
+    act = torch.zeros((32, 64, 2), device=cuda_device)
+    for _ in range(3):
+        obs = mgr.update(act)
+        status, traffic = mgr.check_status()
+    assert (status == int(ScenarioStatus.TIME_EXCEEDED)).all() and te.update(w).all()
+    assert set(np.unique(traffic.cpu().numpy())) <= {int(TrafficStatus.NORMAL), int(TrafficStatus.COLLISION_STATIC), int(TrafficStatus.COLLISION_DYNAMIC)}
+    assert obs["x"].data_ptr() == w.x.data_ptr()   # the observation is a view, not a copy
+    mgr.reset()
+    assert int(w.step_count.max()) == 0 and torch.equal(w.x, pool["x"])
+    w.close()
+
+
+def test_batched_env_contract(cuda_device):
+    import torch
+
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.envs import BatchedTrafficEnv, InvalidAction
+    from tactics2d_b200.traffic import ScenarioStatus
+
+    scene = synthetic.config2(64, 16, seed=8, size=60.0)
+    env = BatchedTrafficEnv(scene, device=cuda_device, max_step=5, auto_reset=True)
+    obs, info = env.reset(seed=3)
+    assert set(obs) == {"x", "y", "heading", "speed", "vx", "vy"} and obs["x"].shape == (64, 16)
+    assert (info["scenario_status"] == int(ScenarioStatus.NORMAL)).all()
+    with pytest.raises(InvalidAction):
+        env.step(torch.zeros((3, 2), device=cuda_device))
+    total_done = 0
+    for t in range(8):
+        action = torch.zeros((64, 2), device=cuda_device)
+        action[:, 0] = 0.1   # steering first
+        action[:, 1] = 1.0   # then acceleration
+        obs, reward, terminated, truncated, info = env.step(action)
+        assert reward.shape == (64,) and terminated.dtype == torch.bool and not terminated.any()
+        st = info["scenario_status"]
+        assert ((st != int(ScenarioStatus.NORMAL)) == truncated).all()
+        assert (reward[st == int(ScenarioStatus.TIME_EXCEEDED)] == -1).all()
+        assert (reward[st == int(ScenarioStatus.OUT_BOUND)] == -5).all() and (reward[st == int(ScenarioStatus.FAILED)] == -5).all()
+        assert (reward[st == int(ScenarioStatus.NORMAL)] > -0.01).all()
+        total_done += int(truncated.sum())
+        # auto-reset: finished scenarios are back at their initial state with a zero step counter
+        assert (env.world.step_count[truncated] == 0).all()
+        assert torch.equal(env.world.x[truncated], env._pool["x"][truncated])
+    assert total_done >= 64   # the 5-step limit ends every scenario at least once
+    # ego speed grew under the (steer, accel) action order: accel = 1 m/s^2 was applied to `speed`
+    env.close()
