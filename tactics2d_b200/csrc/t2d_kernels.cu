@@ -30,10 +30,10 @@
 
 namespace t2d {
 
-constexpr int PPL = 4;                  // participants per lane
+constexpr int MAX_PPL = 4;              // participants per lane: 1, 2 or 4 (template parameter of K1)
 constexpr int MAX_WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host picks 2, 4 or 8 warps per CTA
-constexpr int POSE_PER_WARP = 128;      // 32 lanes x PPL
+constexpr int POSE_PER_WARP = 128;      // 32 lanes x MAX_PPL
 constexpr int MAP_SMEM_LIMIT = 120 * 1024;
 
 struct MapHeader {   // 64 bytes, start of the map blob
@@ -41,8 +41,10 @@ struct MapHeader {   // 64 bytes, start of the map blob
   float x0, y0, inv_cell, cell;
   uint32_t off_seg, off_cell, off_items, total_bytes;
   uint32_t off_clear;   // float per cell: lower bound of the distance from any point of the cell to any segment
-  uint32_t pad[3];
+  int32_t fine;         // the fine clearance field has (gx * fine) x (gy * fine) cells, one byte each (global memory)
+  uint32_t pad[2];
 };
+constexpr float CLEAR_QUANT = 0.125f;   // metres per unit of the byte-quantised fine clearance field
 static_assert(sizeof(MapHeader) == 64, "MapHeader must be 64 bytes");
 
 struct StepArgs {
@@ -56,6 +58,7 @@ struct StepArgs {
   uint8_t* scn_status;
   uint8_t* done;
   const unsigned char* map_blob;   // device; nullptr when no segments
+  const uint8_t* map_fine;         // device; fine clearance field (bytes), read through L1/L2
   const Params* table;             // device
   int map_bytes, map_in_smem;
   int n_types;
@@ -97,6 +100,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------- vector access
+// N consecutive elements of an [N_scn, M] array as ONE load / store of sizeof(T) * N bytes (<= 16).
+template <int BYTES> struct VecOf;
+template <> struct VecOf<1> { using T = uint8_t; };
+template <> struct VecOf<2> { using T = uint16_t; };
+template <> struct VecOf<4> { using T = uint32_t; };
+template <> struct VecOf<8> { using T = uint2; };
+template <> struct VecOf<16> { using T = uint4; };
+
+template <typename T, int N>
+__device__ __forceinline__ void ld_vec(const T* p, T (&o)[N]) {
+  using V = typename VecOf<sizeof(T) * N>::T;
+  const V v = *reinterpret_cast<const V*>(p);
+  memcpy(o, &v, sizeof(V));
+}
+template <typename T, int N>
+__device__ __forceinline__ void st_vec(T* p, const T (&o)[N]) {
+  using V = typename VecOf<sizeof(T) * N>::T;
+  V v;
+  memcpy(&v, o, sizeof(V));
+  *reinterpret_cast<V*>(p) = v;
 }
 
 // ---------------------------------------------------------------------------- pair narrowphase
@@ -161,7 +187,8 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
 
 // Static broadphase, level 1: the clearance field.  One shared-memory load tells whether the pose's
 // bounding circle can reach any segment at all (most participants are nowhere near a wall).
-__device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const unsigned char* mapb) {
+__device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const unsigned char* mapb,
+                                              const uint8_t* fine) {
   const MapHeader* mh = reinterpret_cast<const MapHeader*>(mapb);
   const float r = rbound * 1.0001f + 1e-3f;
   const float fx = (ax - mh->x0) * mh->inv_cell, fy = (ay - mh->y0) * mh->inv_cell;
@@ -171,8 +198,9 @@ __device__ __forceinline__ bool near_segments(const float ax, const float ay, co
     const float ox = fmaxf(fmaxf(-fx, fx - (float)gx), 0.0f), oy = fmaxf(fmaxf(-fy, fy - (float)gy), 0.0f);
     return fmaxf(ox, oy) * mh->cell <= r;
   }
-  const float* clear = reinterpret_cast<const float*>(mapb + mh->off_clear);
-  return clear[(int)fy * gx + (int)fx] <= r;
+  const int k = mh->fine;
+  const int ix = min((int)(fx * (float)k), gx * k - 1), iy = min((int)(fy * (float)k), gy * k - 1);
+  return (float)__ldg(fine + (size_t)iy * (gx * k) + ix) * CLEAR_QUANT <= r;
 }
 
 // Level 2: first (lowest-index) map segment the pose touches, or -1.  Uniform grid over the map tile:
@@ -229,7 +257,7 @@ __device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, const fl
 // warp's queue (bit i of cand: participant t0 + i).  1 <= q - i <= Mh keeps every unordered pair once.
 __device__ __noinline__ void pair_enqueue(unsigned cand, int q, int tj, int t0, int Mh, int mp_shift, const float4* poseA,
                                           const float4* poseB, int* hitmin, unsigned* queue, int* qcount) {
-  for (int i = 0; i < PPL; ++i) {
+  for (int i = 0; i < MAX_PPL; ++i) {
     if (!((cand >> i) & 1u)) continue;
     const int k = q - i;
     if (k < 1 || k > Mh) continue;
@@ -252,7 +280,10 @@ __device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, 
 }
 
 // ---------------------------------------------------------------------------- K1
-__global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_constant__ StepArgs A) {
+// KIN_ONLY: every type in the table is SingleTrackKinematics or static - the fp64 models are compiled out
+// (their register footprint would otherwise bound the occupancy of the whole kernel).
+template <int PPL, bool KIN_ONLY>
+__global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4))) t2d_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   // carve: [map blob | 16B aligned] [type table] [pose tiles] [mbarrier]
   const int map_smem_bytes = A.map_in_smem ? A.map_bytes : 0;
@@ -321,26 +352,33 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
       tidv[i] = T2D_TYPE_INACTIVE;
     }
     if (nvalid == PPL && A.vec_ok) {
-      const float4 X = *reinterpret_cast<const float4*>(A.x + idx0);
-      const float4 Y = *reinterpret_cast<const float4*>(A.y + idx0);
-      const float4 H = *reinterpret_cast<const float4*>(A.h + idx0);
-      const float4 V = *reinterpret_cast<const float4*>(A.v + idx0);
-      const uchar4 T = *reinterpret_cast<const uchar4*>(A.type_id + idx0);
-      sx[0] = X.x; sx[1] = X.y; sx[2] = X.z; sx[3] = X.w;
-      sy[0] = Y.x; sy[1] = Y.y; sy[2] = Y.z; sy[3] = Y.w;
-      shd[0] = H.x; shd[1] = H.y; shd[2] = H.z; shd[3] = H.w;
-      sv[0] = V.x; sv[1] = V.y; sv[2] = V.z; sv[3] = V.w;
-      tidv[0] = T.x; tidv[1] = T.y; tidv[2] = T.z; tidv[3] = T.w;
+      ld_vec<float, PPL>(A.x + idx0, sx);
+      ld_vec<float, PPL>(A.y + idx0, sy);
+      ld_vec<float, PPL>(A.h + idx0, shd);
+      ld_vec<float, PPL>(A.v + idx0, sv);
+      uint8_t tb8[PPL];
+      ld_vec<uint8_t, PPL>(A.type_id + idx0, tb8);
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) tidv[i] = tb8[i];
       if (A.do_physics) {
-        const float4 P0 = *reinterpret_cast<const float4*>(A.action + 2 * idx0);
-        const float4 P1 = *reinterpret_cast<const float4*>(A.action + 2 * idx0 + 4);
-        a0[0] = P0.x; a1[0] = P0.y; a0[1] = P0.z; a1[1] = P0.w;
-        a0[2] = P1.x; a1[2] = P1.y; a0[3] = P1.z; a1[3] = P1.w;
+        float2 act[PPL];
+        if constexpr (PPL == 4) {
+          float lo[4], hi[4];
+          ld_vec<float, 4>(A.action + 2 * idx0, lo);
+          ld_vec<float, 4>(A.action + 2 * idx0 + 4, hi);
+          act[0] = make_float2(lo[0], lo[1]); act[1] = make_float2(lo[2], lo[3]);
+          act[2] = make_float2(hi[0], hi[1]); act[3] = make_float2(hi[2], hi[3]);
+        } else {
+          float raw[2 * PPL];
+          ld_vec<float, 2 * PPL>(A.action + 2 * idx0, raw);
+#pragma unroll
+          for (int i = 0; i < PPL; ++i) act[i] = make_float2(raw[2 * i], raw[2 * i + 1]);
+        }
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) { a0[i] = act[i].x; a1[i] = act[i].y; }
         if (A.needs_vel_in) {
-          const float4 VX = *reinterpret_cast<const float4*>(A.vx + idx0);
-          const float4 VY = *reinterpret_cast<const float4*>(A.vy + idx0);
-          svx[0] = VX.x; svx[1] = VX.y; svx[2] = VX.z; svx[3] = VX.w;
-          svy[0] = VY.x; svy[1] = VY.y; svy[2] = VY.z; svy[3] = VY.w;
+          ld_vec<float, PPL>(A.vx + idx0, svx);
+          ld_vec<float, PPL>(A.vy + idx0, svy);
         }
       }
     } else {
@@ -398,7 +436,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
             kin1_step(io, *pp[i], A.n_steps, A.dt, A.dt_rem);
             sx[i] = io.x[0]; sy[i] = io.y[0]; shd[i] = io.h[0]; sv[i] = io.v[0];
             svx[i] = io.vx[0]; svy[i] = io.vy[0]; ch[i] = io.ch[0]; sh[i] = io.sh[0];
-          } else {
+          } else if constexpr (!KIN_ONLY) {
             OneIO io;
             io.x = sx[i]; io.y = sy[i]; io.h = shd[i]; io.v = sv[i]; io.vx = svx[i]; io.vy = svy[i];
             io.a0 = a0[i]; io.a1 = a1[i];
@@ -406,17 +444,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
             other_model_step(io, *pp[i], A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
             sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
             ch[i] = io.ch; sh[i] = io.sh;
+          } else {
+            sincosf(shd[i], &sh[i], &ch[i]);   // static participant: the pose only
           }
         }
       }
       // ---------------------------------------------------------------- store state
       if (nvalid == PPL && A.vec_ok) {
-        *reinterpret_cast<float4*>(A.x + idx0) = make_float4(sx[0], sx[1], sx[2], sx[3]);
-        *reinterpret_cast<float4*>(A.y + idx0) = make_float4(sy[0], sy[1], sy[2], sy[3]);
-        *reinterpret_cast<float4*>(A.h + idx0) = make_float4(shd[0], shd[1], shd[2], shd[3]);
-        *reinterpret_cast<float4*>(A.v + idx0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
-        *reinterpret_cast<float4*>(A.vx + idx0) = make_float4(svx[0], svx[1], svx[2], svx[3]);
-        *reinterpret_cast<float4*>(A.vy + idx0) = make_float4(svy[0], svy[1], svy[2], svy[3]);
+        st_vec<float, PPL>(A.x + idx0, sx);
+        st_vec<float, PPL>(A.y + idx0, sy);
+        st_vec<float, PPL>(A.h + idx0, shd);
+        st_vec<float, PPL>(A.v + idx0, sv);
+        st_vec<float, PPL>(A.vx + idx0, svx);
+        st_vec<float, PPL>(A.vy + idx0, svy);
       } else {
         for (int i = 0; i < nvalid; ++i) {
           if (!active[i]) continue;
@@ -504,7 +544,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
       }
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
-        if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], mapb))
+        if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], mapb, A.map_fine))
           hseg[i] = static_slow(poseA, poseB, t0 + i, rb[i], mapb);
     }
 
@@ -524,12 +564,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
       fl[i] = f;
     }
     if (nvalid == PPL && A.vec_ok) {
-      if (A.flags) *reinterpret_cast<uchar4*>(A.flags + idx0) = make_uchar4(fl[0], fl[1], fl[2], fl[3]);
-      if (A.hit_index)
-        *reinterpret_cast<short4*>(A.hit_index + idx0) = make_short4((short)hit[0], (short)hit[1], (short)hit[2], (short)hit[3]);
-      if (A.hit_segment)
-        *reinterpret_cast<short4*>(A.hit_segment + idx0) =
-            make_short4((short)hseg[0], (short)hseg[1], (short)hseg[2], (short)hseg[3]);
+      int16_t h16[PPL], s16[PPL];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) { h16[i] = (int16_t)hit[i]; s16[i] = (int16_t)hseg[i]; }
+      if (A.flags) st_vec<uint8_t, PPL>(A.flags + idx0, fl);
+      if (A.hit_index) st_vec<int16_t, PPL>(A.hit_index + idx0, h16);
+      if (A.hit_segment) st_vec<int16_t, PPL>(A.hit_segment + idx0, s16);
     } else {
       for (int i = 0; i < nvalid; ++i) {
         if (A.flags) A.flags[idx0 + i] = fl[i];
@@ -542,7 +582,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) t2d_step_kernel(const __grid_c
     if (A.do_physics) {
       unsigned agg;
       if (A.cfg_flags & T2D_CFG_ANY_PARTICIPANT) {
-        agg = fl[0] | fl[1] | fl[2] | fl[3];
+        agg = 0;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) agg |= fl[i];
         for (int o = G >> 1; o > 0; o >>= 1) agg |= __shfl_xor_sync(0xffffffffu, agg, o);
       } else {
         agg = __shfl_sync(0xffffffffu, (unsigned)fl[0], sub * G);   // participant 0 = the ego
@@ -643,12 +685,14 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 struct t2d_ctx {
-  int device = 0, N = 0, M = 0, G = 0;
+  int device = 0, N = 0, M = 0, G = 0, ppl = 4;
   t2d_config cfg{};
   int n_types = 0;
   bool has_pointmass = false;
+  bool kin_only = false;
   Params* d_table = nullptr;
   unsigned char* d_map = nullptr;
+  uint8_t* d_fine = nullptr;
   int map_bytes = 0;
   bool has_bounds = false;
   float bounds[4] = {0, 0, 0, 0};
@@ -691,8 +735,16 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   c->device = device;
   c->N = n_scenarios;
   c->M = m_participants;
+  // participants per lane: the smallest of 1 / 2 / 4 that lets one warp span a scenario (more warps in
+  // flight for the same batch), overridable with T2D_PPL for experiments
+  int ppl = m_participants <= 32 ? 1 : (m_participants <= 64 ? 2 : 4);
+  if (const char* e = getenv("T2D_PPL")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && 32 * v >= m_participants) ppl = v;
+  }
+  c->ppl = ppl;
   int g = 1;
-  while (g * PPL < m_participants) g <<= 1;
+  while (g * ppl < m_participants) g <<= 1;
   c->G = g;
   c->cfg = *cfg;
   cudaDeviceProp prop;
@@ -708,6 +760,7 @@ int t2d_destroy(t2d_ctx* c) {
   cudaSetDevice(c->device);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_map) cudaFree(c->d_map);
+  if (c->d_fine) cudaFree(c->d_fine);
   delete c;
   return T2D_OK;
 }
@@ -744,6 +797,11 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   CUDA_TRY(cudaMemcpy(c->d_table, table, n_types * sizeof(Params), cudaMemcpyHostToDevice));
   c->n_types = n_types;
   c->rb_max = rb_max;
+  c->kin_only = true;
+  for (int i = 0; i < n_types; ++i)
+    if (table[i].model != T2D_MODEL_KINEMATICS && table[i].model != T2D_MODEL_STATIC) c->kin_only = false;
+  c->configured_smem = -1;
+  for (int w = 0; w < 9; ++w) c->occ_smem[w] = -1;
   return T2D_OK;
 }
 
@@ -762,6 +820,10 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   if (c->d_map) {
     cudaFree(c->d_map);
     c->d_map = nullptr;
+  }
+  if (c->d_fine) {
+    cudaFree(c->d_fine);
+    c->d_fine = nullptr;
   }
   c->map_bytes = 0;
   if (n_seg == 0) return T2D_OK;
@@ -824,25 +886,48 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
     for (uint16_t s : cells[ci]) it[acc++] = s;
   }
   cs[cells.size()] = acc;
-  // clearance field: distance from the cell centre to the nearest segment, minus the cell's half diagonal
-  float* clr = reinterpret_cast<float*>(blob.data() + mh.off_clear);
-  const double half_diag = 0.5 * std::sqrt(2.0) * (double)cell * 1.0001 + 2.0 * margin;
-  for (int cy = 0; cy < gy; ++cy)
-    for (int cx = 0; cx < gx; ++cx) {
-      const double px = (double)x0 + (cx + 0.5) * (double)cell, py = (double)y0 + (cy + 0.5) * (double)cell;
-      double best = INFINITY;
-      for (int i = 0; i < n_seg; ++i) {
-        const float* sg = segments + 4 * i;
-        const double dx = (double)sg[2] - sg[0], dy = (double)sg[3] - sg[1], ux = px - sg[0], uy = py - sg[1];
-        const double dd = dx * dx + dy * dy;
-        double t = dd > 0.0 ? (ux * dx + uy * dy) / dd : 0.0;
-        t = std::min(1.0, std::max(0.0, t));
-        const double ex = ux - t * dx, ey = uy - t * dy;
-        best = std::min(best, ex * ex + ey * ey);
-      }
-      const double d = std::sqrt(best) - half_diag;
-      clr[(size_t)cy * gx + cx] = d > 0.0 ? (float)(d * 0.9999) : 0.0f;
+  // clearance fields: lower bound of the distance from any point of a cell to the nearest segment
+  // (distance from the cell centre minus the half diagonal).  Coarse (float, in the blob) and fine
+  // (bytes of CLEAR_QUANT metres, 4 x 4 per coarse cell, in global memory).
+  auto centre_dist = [&](double px, double py) {
+    double best = INFINITY;
+    for (int i = 0; i < n_seg; ++i) {
+      const float* sg = segments + 4 * i;
+      const double dx = (double)sg[2] - sg[0], dy = (double)sg[3] - sg[1], ux = px - sg[0], uy = py - sg[1];
+      const double dd = dx * dx + dy * dy;
+      double t = dd > 0.0 ? (ux * dx + uy * dy) / dd : 0.0;
+      t = std::min(1.0, std::max(0.0, t));
+      const double ex = ux - t * dx, ey = uy - t * dy;
+      best = std::min(best, ex * ex + ey * ey);
     }
+    return std::sqrt(best);
+  };
+  float* clr = reinterpret_cast<float*>(blob.data() + mh.off_clear);
+  {
+    const double half_diag = 0.5 * std::sqrt(2.0) * (double)cell * 1.0001 + 2.0 * margin;
+    for (int cy = 0; cy < gy; ++cy)
+      for (int cx = 0; cx < gx; ++cx) {
+        const double d = centre_dist((double)x0 + (cx + 0.5) * (double)cell, (double)y0 + (cy + 0.5) * (double)cell) - half_diag;
+        clr[(size_t)cy * gx + cx] = d > 0.0 ? (float)(d * 0.9999) : 0.0f;
+      }
+  }
+  int fine = 4;   // bounded host work: cells x segments <= ~1e8 distance evaluations
+  while (fine > 1 && (double)gx * gy * fine * fine * n_seg > 1e8) fine >>= 1;
+  mh.fine = fine;
+  memcpy(blob.data(), &mh, sizeof(mh));
+  std::vector<uint8_t> fine_field((size_t)gx * fine * gy * fine);
+  {
+    const double fc = (double)cell / fine;
+    const double half_diag = 0.5 * std::sqrt(2.0) * fc * 1.001 + 2.0 * margin + 1e-3 * fc;
+    for (int iy = 0; iy < gy * fine; ++iy)
+      for (int ix = 0; ix < gx * fine; ++ix) {
+        const double d = centre_dist((double)x0 + (ix + 0.5) * fc, (double)y0 + (iy + 0.5) * fc) - half_diag;
+        const double q = std::floor(std::max(0.0, d) / CLEAR_QUANT);
+        fine_field[(size_t)iy * gx * fine + ix] = (uint8_t)std::min(255.0, q);
+      }
+  }
+  CUDA_TRY(cudaMalloc(&c->d_fine, fine_field.size()));
+  CUDA_TRY(cudaMemcpy(c->d_fine, fine_field.data(), fine_field.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&c->d_map, mh.total_bytes));
   CUDA_TRY(cudaMemcpy(c->d_map, blob.data(), mh.total_bytes, cudaMemcpyHostToDevice));
   c->map_bytes = (int)mh.total_bytes;
@@ -873,7 +958,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.type_id = c->type_id; A.step_count = c->step_count;
   A.action = action; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
   A.scn_status = scn_status; A.done = done;
-  A.map_blob = c->d_map; A.map_bytes = c->map_bytes;
+  A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine;
   A.map_in_smem = (c->d_map && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
   A.table = c->d_table; A.n_types = c->n_types;
   A.N = c->N; A.M = c->M; A.G = c->G;
@@ -888,7 +973,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.do_physics = do_physics; A.has_bounds = c->has_bounds ? 1 : 0;
   A.bxmin = c->bounds[0]; A.bxmax = c->bounds[1]; A.bymin = c->bounds[2]; A.bymax = c->bounds[3];
   A.needs_vel_in = c->has_pointmass ? 1 : 0;
-  bool vec = (c->M % 4 == 0) && aligned16(A.x) && aligned16(A.y) && aligned16(A.h) && aligned16(A.v) && aligned16(A.vx) &&
+  bool vec = (c->M % c->ppl == 0) && aligned16(A.x) && aligned16(A.y) && aligned16(A.h) && aligned16(A.v) && aligned16(A.vx) &&
              aligned16(A.vy) && (reinterpret_cast<uintptr_t>(A.type_id) % 4 == 0) && (!action || aligned16(action)) &&
              (!flags || reinterpret_cast<uintptr_t>(flags) % 4 == 0) && (!hit_index || reinterpret_cast<uintptr_t>(hit_index) % 8 == 0) &&
              (!hit_segment || reinterpret_cast<uintptr_t>(hit_segment) % 8 == 0);
@@ -907,20 +992,26 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   const int smem_fixed = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 16;
   const int smem = smem_fixed + wpc * (POSE_PER_WARP * (2 * (int)sizeof(float4) + (int)sizeof(int)) + QCAP * 4) + 32;
   if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");
+  using kernel_t = void (*)(StepArgs);
+  kernel_t kern;
+  if (c->kin_only)
+    kern = c->ppl == 1 ? (kernel_t)t2d_step_kernel<1, true> : (c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, true> : (kernel_t)t2d_step_kernel<4, true>);
+  else
+    kern = c->ppl == 1 ? (kernel_t)t2d_step_kernel<1, false> : (c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, false> : (kernel_t)t2d_step_kernel<4, false>);
   if (smem > c->configured_smem) {
-    CUDA_TRY(cudaFuncSetAttribute(t2d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->configured_smem = smem;
   }
   const long long ctas_needed = (tiles + wpc - 1) / wpc;
   if (c->occ_smem[wpc] != smem) {
     int per_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2d_step_kernel, wpc * 32, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     c->occ_val[wpc] = per_sm < 1 ? 1 : per_sm;
     c->occ_smem[wpc] = smem;
   }
   const long long resident = (long long)c->sm_count * c->occ_val[wpc];
   const int grid = (int)std::max(1LL, std::min(ctas_needed, resident));
-  t2d_step_kernel<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(A);
+  kern<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;

@@ -1,0 +1,65 @@
+"""Scenario-axis sharding across ranks (one process per GPU).
+
+Scenarios never interact (the reference runs one ``ScenarioManager`` per env, scenario_manager.py:52-61), so
+the N scenarios are split into contiguous blocks, one per rank, with no data-path collective inside the tick.
+The single exchange per step is the all-gather of the ``uint8 done`` mask (a centralised learner / reset
+scheduler needs every rank's mask).  Works on any ``torch.distributed`` backend: NCCL on the GPUs, gloo in the
+CPU tests of the host logic.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+
+def shard_range(n_total: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of scenarios owned by ``rank``; block sizes differ by at most one and the
+    participants of a scenario are never split."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_total, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_total: int, world_size: int):
+    return [shard_range(n_total, r, world_size)[1] - shard_range(n_total, r, world_size)[0] for r in range(world_size)]
+
+
+class DoneExchange:
+    """All-gather of the per-rank ``done`` masks into one [N_total] tensor on every rank.
+
+    Equal shards use ``all_gather_into_tensor`` (one NCCL call, graph-capturable); unequal shards pad to the
+    largest shard.  ``group`` is a ``torch.distributed`` process group (default: WORLD)."""
+
+    def __init__(self, n_total: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_total = n_total
+        self.sizes = shard_sizes(n_total, self.world_size)
+        self.lo, self.hi = shard_range(n_total, self.rank, self.world_size)
+        self.equal = len(set(self.sizes)) == 1
+        self.pad = max(self.sizes)
+        self._gathered = torch.zeros(self.world_size * self.pad, dtype=torch.uint8, device=device)
+        self._send = torch.zeros(self.pad, dtype=torch.uint8, device=device)
+        self.out = self._gathered if self.equal else torch.zeros(n_total, dtype=torch.uint8, device=device)
+
+    def __call__(self, done_local):
+        """``done_local``: uint8 [hi - lo] on this rank -> uint8 [N_total] (same tensor object every call)."""
+        if done_local.numel() != self.hi - self.lo:
+            raise ValueError("done_local does not match this rank's shard")
+        if self.equal:
+            self.dist.all_gather_into_tensor(self._gathered, done_local, group=self.group)
+            return self._gathered
+        self._send[: done_local.numel()].copy_(done_local)
+        self.dist.all_gather_into_tensor(self._gathered, self._send, group=self.group)
+        off = 0
+        for r, sz in enumerate(self.sizes):
+            self.out[off:off + sz].copy_(self._gathered[r * self.pad:r * self.pad + sz])
+            off += sz
+        return self.out

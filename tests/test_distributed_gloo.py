@@ -1,0 +1,83 @@
+"""N > 1 host logic on CPU: scenario sharding and the done-mask exchange, world_size 2 over gloo."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tactics2d_b200.distributed import shard_range, shard_sizes
+
+
+def test_shard_ranges_cover_and_never_split():
+    for n, w in [(4096, 8), (4096, 3), (7, 2), (5, 8), (16384, 8)]:
+        ranges = [shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(w - 1))
+        sizes = shard_sizes(n, w)
+        assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_total, q):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import scenario as O
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.distributed import DoneExchange, shard_range
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        scene = synthetic.config2(n_total, 16, seed=5, size=40.0)      # every rank builds the same global scene
+        lo, hi = shard_range(n_total, rank, world)
+        table = scene.table.as_oracle_table()
+        act = synthetic.random_actions(3, scene.shape)
+        # this rank's shard of the tick (oracle stands in for the kernel: the host logic is what is under test)
+        st = {k: v[lo:hi] for k, v in scene.state().items()}
+        _, fl, _, _, _, done, _ = O.tick(st, scene.type_id[lo:hi], act[lo:hi], table, np.zeros(hi - lo, np.int32), scene.segments,
+                                         scene.bounds, ego_only=False)
+        ex = DoneExchange(n_total, torch.device("cpu"))
+        got = ex(torch.from_numpy(done)).clone().numpy()
+        got2 = ex(torch.from_numpy(done)).numpy()                    # second call reuses the buffers
+        q.put((rank, got, got2, done, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [12, 13])
+def test_done_mask_all_gather_world2(n_total):
+    import torch.multiprocessing as mp
+
+    from oracle import scenario as O
+    from tactics2d_b200 import synthetic
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process truth over the whole batch
+    scene = synthetic.config2(n_total, 16, seed=5, size=40.0)
+    act = synthetic.random_actions(3, scene.shape)
+    _, _, _, _, _, done_all, _ = O.tick(scene.state(), scene.type_id, act, scene.table.as_oracle_table(), np.zeros(n_total, np.int32),
+                                        scene.segments, scene.bounds, ego_only=False)
+    assert done_all.any() and not done_all.all()
+    for rank, got, got2, local, (lo, hi) in results:
+        assert np.array_equal(got, done_all) and np.array_equal(got2, done_all)
+        assert np.array_equal(local, done_all[lo:hi])

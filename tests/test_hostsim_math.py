@@ -1,0 +1,232 @@
+"""The device arithmetic (tactics2d_b200/csrc/t2d_math.cuh), compiled for the host by tests/hostsim, against the
+float64 oracle and the reference's golden vectors - the fp32 / filtered-predicate numerics checked without a GPU.
+(The harness is test infrastructure; the product has no CPU path.)"""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+from oracle import physics as P
+from tactics2d_b200 import TypeParams, TypeTable
+from tests.util import heading_err, rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RNG = dict(steer_lo=-0.524, steer_hi=0.524, speed_lo=-16.67, speed_hi=69.44, accel_lo=-11.0, accel_hi=3.121)
+MEDIUM = dict(lf=4.284 / 2 - 0.880, lr=4.284 / 2 - 0.767)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def run_physics(hs, table, tid, x, y, h, v, vx, vy, act, interval=100, delta_t=5):
+    arrs = [np.ascontiguousarray(a, dtype=np.float32).copy() for a in (x, y, h, v, vx, vy)]
+    act = np.ascontiguousarray(act, dtype=np.float32)
+    app = np.zeros_like(act)
+    tid = np.ascontiguousarray(tid, dtype=np.int32)
+    hs.hs_physics(C.c_int(len(tid)), table.to_c_array(), _p(tid), C.c_int(interval // delta_t), C.c_double(delta_t / 1000),
+                  C.c_double((interval % delta_t) / 1000), C.c_double(interval / 1000), *[_p(a) for a in arrs], _p(act), _p(app))
+    return [a.astype(np.float64) for a in arrs], app.astype(np.float64)
+
+
+def _check(got, app, ref, sel=None):
+    sel = slice(None) if sel is None else sel
+    x, y, h, v, vx, vy = got
+    vs = np.maximum(np.abs(ref[:, 3]), 1.0)
+    errs = dict(x=rel_err(x, ref[:, 0])[sel].max(), y=rel_err(y, ref[:, 1])[sel].max(), h=heading_err(h, ref[:, 2])[sel].max(),
+                v=rel_err(v, ref[:, 3])[sel].max(), vx=rel_err(vx, ref[:, 4], vs)[sel].max(), vy=rel_err(vy, ref[:, 5], vs)[sel].max(),
+                a=rel_err(app[:, 0], ref[:, 6])[sel].max(), d=rel_err(app[:, 1], ref[:, 7])[sel].max())
+    return errs
+
+
+def test_bicycles_vs_reference_golden(hostsim):
+    g = np.load(os.path.join(GOLD, "physics_bicycle.npz"))
+    st, ac = g["states"], g["actions"]
+    worst = {}
+    for key in g.files:
+        if not (key.startswith("kin_") or key.startswith("dyn_")):
+            continue
+        tag, name, interval, dt = key.split("_")
+        interval = int(interval)
+        dt = P.effective_delta_t(None if dt == "None" else int(dt), interval)
+        kw = dict(MEDIUM, **(RNG if name == "con" else {}))
+        if tag == "dyn":
+            kw.update(mass=float(g["mass"]), mass_height=float(g["mass_height"]), model=1)
+        table = TypeTable([TypeParams(**kw)])
+        got, app = run_physics(hostsim, table, np.zeros(len(st)), st[:, 0], st[:, 1], st[:, 2], st[:, 3], 0 * st[:, 0], 0 * st[:, 0], ac,
+                               interval, dt)
+        sel = None
+        if tag == "dyn":   # outside the band where the reference's explicit Euler is unstable
+            v_end = st[:, 3] + np.clip(ac[:, 0], kw.get("accel_lo", -np.inf), kw.get("accel_hi", np.inf)) * interval / 1000
+            # forward >= 0.7 m/s, or reversing faster than 3 m/s (in reverse the slip-angle equation grows by
+            # (1 + 0.72/|v|) per sub-step, which amplifies the fp32 rounding of the golden float64 inputs)
+            sel = ((st[:, 3] >= 0.7) & (v_end >= 0.7)) | ((st[:, 3] <= -3.0) & (v_end <= -3.0))
+        e = _check(got, app, g[key], sel)
+        for k, v in e.items():
+            worst[k] = max(worst.get(k, 0), v)
+        assert max(e.values()) <= 1e-5, (key, e)
+    assert worst["x"] < 5e-6
+
+
+def test_kinematics_4wide_equals_1wide_and_oracle(hostsim):
+    rng = np.random.default_rng(0)
+    n = 4096
+    p = TypeParams(**MEDIUM, **RNG)
+    table = TypeTable([p])
+    x, y = rng.uniform(-1000, 1000, n), rng.uniform(-1000, 1000, n)
+    h, v = rng.uniform(0, 2 * np.pi, n), rng.uniform(-16, 69, n)
+    act = np.stack([rng.uniform(-14, 6, n), rng.uniform(-0.8, 0.8, n)], 1)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    x, y, h, v, act = f32(x), f32(y), f32(h), f32(v), f32(act)
+    (x1, y1, h1, v1, vx1, vy1), _ = run_physics(hostsim, table, np.zeros(n), x, y, h, v, 0 * x, 0 * x, act)
+    arrs = [a.copy() for a in (x, y, h, v, 0 * x, 0 * x)]
+    c = p.to_c()
+    hostsim.hs_kinematics4(C.c_int(n), C.byref(c), C.c_int(20), C.c_double(0.005), C.c_double(0.0), *[_p(a) for a in arrs], _p(act))
+    for a, b in zip(arrs, (x1, y1, h1, v1, vx1, vy1)):
+        assert np.array_equal(a.astype(np.float64), b)   # the ILP-4 path is the same arithmetic
+    t = table.as_oracle_table()
+    o = P.step_kinematics(x, y, h, v, act[:, 0], act[:, 1], t["lf"][0], t["lr"][0], (t["steer_lo"][0], t["steer_hi"][0]),
+                          (t["speed_lo"][0], t["speed_hi"][0]), (t["accel_lo"][0], t["accel_hi"][0]))
+    assert rel_err(x1, o["x"]).max() < 5e-6 and rel_err(y1, o["y"]).max() < 5e-6 and heading_err(h1, o["heading"]).max() < 3e-6
+    assert rel_err(v1, o["speed"]).max() < 1e-6
+
+
+def test_kinematics_large_rotation_fallback(hostsim):
+    """Unconstrained speeds: per-sub-step rotation beyond the polynomial's range takes the exact-trig path."""
+    rng = np.random.default_rng(1)
+    n = 512
+    table = TypeTable([TypeParams(**MEDIUM)])
+    x = np.zeros(n, np.float32)
+    v = rng.uniform(150, 400, n).astype(np.float32)
+    h = rng.uniform(0, 6.28, n).astype(np.float32)
+    act = np.stack([rng.uniform(-5, 5, n), rng.uniform(-0.7, 0.7, n)], 1).astype(np.float32)
+    (x1, y1, h1, v1, _, _), _ = run_physics(hostsim, table, np.zeros(n), x, x, h, v, x, x, act)
+    o = P.step_kinematics(x, x, h, v, act[:, 0], act[:, 1], table.as_oracle_table()["lf"][0], table.as_oracle_table()["lr"][0],
+                          (-np.inf, np.inf), (-np.inf, np.inf), (-np.inf, np.inf))
+    assert np.abs(x1 - o["x"]).max() < 2e-4 and np.abs(y1 - o["y"]).max() < 2e-4 and heading_err(h1, o["heading"]).max() < 2e-5
+
+
+def test_pointmass_vs_reference_golden(hostsim):
+    g = np.load(os.path.join(GOLD, "physics_pointmass.npz"))
+    st, ac = g["states"], g["actions"]
+    ranges = {"ped": (-7.0, 7.0), "band": (1.0, 3.0), "flt": 4.0, "unc": None}
+    for key in g.files:
+        if not key.startswith("pm_"):
+            continue
+        _, name, backend, interval, dt = key.split("_")
+        lo, hi = P.normalize_range_pointmass(ranges[name])
+        table = TypeTable([TypeParams(speed_lo=lo, speed_hi=hi, model=3 if backend == "euler" else 2, shape=1)])
+        h0 = np.arctan2(st[:, 3], st[:, 2])
+        (x, y, h, v, vx, vy), _ = run_physics(hostsim, table, np.zeros(len(st)), st[:, 0], st[:, 1], h0, 0 * h0, st[:, 2], st[:, 3], ac,
+                                              int(interval), int(dt))
+        ref = g[key]
+        moving = ref[:, 5] > 1e-3
+        vs = np.maximum(ref[:, 5], 1.0)
+        assert rel_err(x, ref[:, 0]).max() <= 1e-5 and rel_err(y, ref[:, 1]).max() <= 1e-5, key
+        assert heading_err(h[moving], ref[moving, 2]).max() <= 2e-5, key
+        assert rel_err(vx, ref[:, 3], vs).max() <= 1e-5 and rel_err(vy, ref[:, 4], vs).max() <= 1e-5, key
+        assert rel_err(v, ref[:, 5]).max() <= 1e-5, key
+
+
+def test_wrap_two_pi(hostsim):
+    hostsim.hs_wrap.restype = C.c_float
+    for phi in [0.0, -1e-7, 6.2831853, 6.283186, 12.6, -3.0, 100.0, -100.0, 6.2831855]:
+        r = hostsim.hs_wrap(C.c_float(phi))
+        assert 0.0 <= r < 2 * np.pi
+        assert heading_err(r, np.mod(np.float64(np.float32(phi)), 2 * np.pi)) < 2e-5 * max(1, abs(phi))
+
+
+def _poses(rng, n, near):
+    """Random pose pairs, a fraction of them within ~1e-5 m of contact, fp32 rounded."""
+    a = np.zeros((n, 5), np.float32)
+    b = np.zeros((n, 5), np.float32)
+    for arr in (a, b):
+        arr[:, 0:2] = rng.uniform(-500, 500, (n, 2))
+        arr[:, 2] = rng.uniform(0, 2 * np.pi, n)
+        arr[:, 3] = rng.uniform(0.1, 3.0, n)
+        arr[:, 4] = np.where(rng.uniform(0, 1, n) < 0.3, -1.0, rng.uniform(0.1, 1.2, n))
+    b[:, 0:2] = a[:, 0:2] + rng.uniform(-6, 6, (n, 2)).astype(np.float32)
+    return a, b
+
+
+def _oracle_pairs(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    ca, sa, cb, sb = np.cos(a[:, 2]), np.sin(a[:, 2]), np.cos(b[:, 2]), np.sin(b[:, 2])
+    ka, kb = a[:, 4] < 0, b[:, 4] < 0
+    oo = G.obb_obb(a[:, 0], a[:, 1], ca, sa, a[:, 3], a[:, 4], b[:, 0], b[:, 1], cb, sb, b[:, 3], b[:, 4])
+    oc = G.obb_circle(a[:, 0], a[:, 1], ca, sa, a[:, 3], a[:, 4], b[:, 0], b[:, 1], b[:, 3])
+    co = G.obb_circle(b[:, 0], b[:, 1], cb, sb, b[:, 3], b[:, 4], a[:, 0], a[:, 1], a[:, 3])
+    cc = G.circle_circle(a[:, 0], a[:, 1], a[:, 3], b[:, 0], b[:, 1], b[:, 3])
+    return np.where(ka, np.where(kb, cc, co), np.where(kb, oc, oo))
+
+
+def test_filtered_pair_predicates_are_exact(hostsim):
+    """The fp32 filter never contradicts the float64 predicate: a definite verdict equals the oracle, and
+    the exact twin always equals the oracle; the undecided band is narrow."""
+    rng = np.random.default_rng(5)
+    n = 400000
+    a, b = _poses(rng, n, 0.0)
+    f32 = np.zeros(n, np.int32)
+    ex = np.zeros(n, np.int32)
+    hostsim.hs_pairs(C.c_int(n), _p(a), _p(b), _p(f32), _p(ex))
+    ref = _oracle_pairs(a, b)
+    assert np.array_equal(ex.astype(bool), ref)
+    decided = f32 >= 0
+    assert np.array_equal(f32[decided].astype(bool), ref[decided])
+    assert 0.05 < ref.mean() < 0.6 and (~decided).mean() < 2e-4
+
+
+def test_filtered_pair_predicates_near_contact(hostsim):
+    """Pairs pushed to within +-2e-5 m of contact along the centre line: the filter must hand them to fp64."""
+    rng = np.random.default_rng(6)
+    n = 20000
+    a = np.zeros((n, 5), np.float32)
+    b = np.zeros((n, 5), np.float32)
+    a[:, 3], a[:, 4], b[:, 3], b[:, 4] = 2.142, 0.8995, 2.142, 0.8995
+    a[:, 0:2] = rng.uniform(-300, 300, (n, 2))
+    gap = rng.uniform(-2e-5, 2e-5, n)
+    b[:, 0] = a[:, 0] + np.float32(2 * 2.142) + gap.astype(np.float32)   # bumper to bumper, heading 0
+    b[:, 1] = a[:, 1] + rng.uniform(-1.5, 1.5, n).astype(np.float32)
+    f32 = np.zeros(n, np.int32)
+    ex = np.zeros(n, np.int32)
+    hostsim.hs_pairs(C.c_int(n), _p(a), _p(b), _p(f32), _p(ex))
+    ref = _oracle_pairs(a, b)
+    assert np.array_equal(ex.astype(bool), ref) and 0.2 < ref.mean() < 0.8
+    decided = f32 >= 0
+    assert np.array_equal(f32[decided].astype(bool), ref[decided])
+    assert (~decided).mean() > 0.5   # most of this band is (rightly) undecided in fp32
+
+
+def test_filtered_segment_and_outbound_predicates(hostsim):
+    rng = np.random.default_rng(7)
+    n = 300000
+    a, _ = _poses(rng, n, 0.0)
+    seg = np.zeros((n, 4), np.float32)
+    seg[:, 0:2] = a[:, 0:2] + rng.uniform(-8, 8, (n, 2)).astype(np.float32)
+    seg[:, 2:4] = seg[:, 0:2] + rng.uniform(-20, 20, (n, 2)).astype(np.float32)
+    seg[:100, 2:4] = seg[:100, 0:2]   # degenerate segments
+    f32 = np.zeros(n, np.int32)
+    ex = np.zeros(n, np.int32)
+    hostsim.hs_segments(C.c_int(n), _p(a), _p(seg), _p(f32), _p(ex))
+    A, S = a.astype(np.float64), seg.astype(np.float64)
+    c, s = np.cos(A[:, 2]), np.sin(A[:, 2])
+    ref = np.where(A[:, 4] < 0, G.circle_segment(A[:, 0], A[:, 1], A[:, 3], S[:, 0], S[:, 1], S[:, 2], S[:, 3]),
+                   G.obb_segment(A[:, 0], A[:, 1], c, s, A[:, 3], A[:, 4], S[:, 0], S[:, 1], S[:, 2], S[:, 3]))
+    assert np.array_equal(ex.astype(bool), ref)
+    d = f32 >= 0
+    assert np.array_equal(f32[d].astype(bool), ref[d]) and (~d).mean() < 1e-3 and 0.05 < ref.mean() < 0.7
+    # out of bound
+    bounds = np.array([-400.0, 400.0, -300.0, 350.0], np.float32)
+    a[: n // 2, 0] = np.where(rng.uniform(0, 1, n // 2) < 0.5, -400, 400) + rng.uniform(-4, 4, n // 2)
+    hostsim.hs_outbound(C.c_int(n), _p(a), _p(bounds), _p(f32), _p(ex))
+    A = a.astype(np.float64)
+    c, s = np.cos(A[:, 2]), np.sin(A[:, 2])
+    circ = A[:, 4] < 0
+    exx, eyy = G.extents(c, s, A[:, 3], A[:, 4])
+    ref = G.out_of_bound(A[:, 0], A[:, 1], np.where(circ, A[:, 3], exx), np.where(circ, A[:, 3], eyy), bounds.astype(np.float64))
+    assert np.array_equal(ex.astype(bool), ref)
+    d = f32 >= 0
+    assert np.array_equal(f32[d].astype(bool), ref[d]) and 0.1 < ref.mean() < 0.9

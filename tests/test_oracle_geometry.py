@@ -1,0 +1,137 @@
+"""The collision oracle (oracle/geometry.py) against an INDEPENDENT exact-rational statement of GEOS's closed-set
+semantics: two polygons `intersect` iff two edges share a point or a vertex of one lies in the (closed) other; a
+segment `intersects` a polygon iff it meets an edge or an endpoint lies inside; a polygon is `contained` in a box iff
+all its vertices are in the closed box.  Rotations are exact (Pythagorean triples), coordinates are small rationals,
+so touching configurations are decided exactly."""
+
+from fractions import Fraction as F
+from itertools import product
+
+import numpy as np
+
+from oracle import geometry as G
+
+TRIPLES = [(F(1), F(0)), (F(0), F(1)), (F(3, 5), F(4, 5)), (F(4, 5), F(3, 5)), (F(5, 13), F(12, 13)), (F(-3, 5), F(4, 5)),
+           (F(8, 17), F(-15, 17)), (F(-1), F(0))]
+
+
+def corners(x, y, c, s, l, w):
+    return [(x + cx * c - cy * s, y + cx * s + cy * c) for cx, cy in ((l, -w), (l, w), (-l, w), (-l, -w))]
+
+
+def orient(a, b, p):
+    v = (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+    return (v > 0) - (v < 0)
+
+
+def on_seg(a, b, p):
+    return min(a[0], b[0]) <= p[0] <= max(a[0], b[0]) and min(a[1], b[1]) <= p[1] <= max(a[1], b[1])
+
+
+def seg_seg(a, b, c, d):
+    o1, o2, o3, o4 = orient(a, b, c), orient(a, b, d), orient(c, d, a), orient(c, d, b)
+    if o1 != o2 and o3 != o4:
+        return True
+    return (o1 == 0 and on_seg(a, b, c)) or (o2 == 0 and on_seg(a, b, d)) or (o3 == 0 and on_seg(c, d, a)) or (o4 == 0 and on_seg(c, d, b))
+
+
+def in_convex(poly, p):
+    signs = [orient(poly[i], poly[(i + 1) % 4], p) for i in range(4)]
+    return all(s >= 0 for s in signs) or all(s <= 0 for s in signs)
+
+
+def exact_poly_poly(A, B):
+    if any(seg_seg(A[i], A[(i + 1) % 4], B[j], B[(j + 1) % 4]) for i in range(4) for j in range(4)):
+        return True
+    return in_convex(B, A[0]) or in_convex(A, B[0])
+
+
+def exact_poly_seg(A, p, q):
+    return any(seg_seg(A[i], A[(i + 1) % 4], p, q) for i in range(4)) or in_convex(A, p)
+
+
+def f(v):
+    return float(v)
+
+
+def test_obb_obb_matches_exact_definition_including_touching():
+    rng = np.random.default_rng(0)
+    n_touch = n_hit = n_total = 0
+    for _ in range(1500):
+        (ca, sa), (cb, sb) = TRIPLES[rng.integers(len(TRIPLES))], TRIPLES[rng.integers(len(TRIPLES))]
+        la, wa, lb, wb = (F(int(rng.integers(1, 9)), 4) for _ in range(4))
+        xa, ya = F(int(rng.integers(-8, 9)), 2), F(int(rng.integers(-8, 9)), 2)
+        xb, yb = xa + F(int(rng.integers(-12, 13)), 4), ya + F(int(rng.integers(-12, 13)), 4)
+        A, B = corners(xa, ya, ca, sa, la, wa), corners(xb, yb, cb, sb, lb, wb)
+        want = exact_poly_poly(A, B)
+        got = bool(G.obb_obb(f(xa), f(ya), f(ca), f(sa), f(la), f(wa), f(xb), f(yb), f(cb), f(sb), f(lb), f(wb)))
+        # only axis-aligned / dyadic cases are exact in float; for the others skip knife-edge configurations
+        exact_float = all(v.denominator in (1, 2, 4, 8) for v in (ca, sa, cb, sb))
+        if exact_float:
+            assert got == want, (A, B)
+            n_total += 1
+            n_hit += want
+            # touching: shrink B slightly -> disjoint would flip if it was only touching
+        elif got != want:
+            # must be a knife-edge: perturbing B by 1e-9 flips the exact answer
+            far = exact_poly_poly(A, corners(xb + F(1, 10**6), yb + F(1, 10**6), cb, sb, lb, wb)) != exact_poly_poly(
+                A, corners(xb - F(1, 10**6), yb - F(1, 10**6), cb, sb, lb, wb))
+            assert far, (A, B)
+    assert n_total > 100 and 0 < n_hit < n_total
+    # explicit closed-set cases: edge touch, corner touch, containment
+    assert G.obb_obb(0, 0, 1, 0, 2, 1, 4, 0, 1, 0, 2, 1)          # edge to edge
+    assert G.obb_obb(0, 0, 1, 0, 2, 1, 4, 2, 1, 0, 2, 1)          # corner to corner
+    assert not G.obb_obb(0, 0, 1, 0, 2, 1, 4.0000001, 0, 1, 0, 2, 1)
+    assert G.obb_obb(0, 0, 1, 0, 4, 4, 0.5, 0.5, 0.6, 0.8, 1, 0.5)  # wholly inside
+
+
+def test_obb_segment_and_disc_predicates_match_exact_definition():
+    rng = np.random.default_rng(1)
+    n = 0
+    for _ in range(1500):
+        c, s = [(F(1), F(0)), (F(0), F(1)), (F(-1), F(0))][rng.integers(3)]
+        l, w = F(int(rng.integers(1, 9)), 4), F(int(rng.integers(1, 9)), 4)
+        x, y = F(int(rng.integers(-8, 9)), 2), F(int(rng.integers(-8, 9)), 2)
+        p = (x + F(int(rng.integers(-16, 17)), 4), y + F(int(rng.integers(-16, 17)), 4))
+        q = (p[0] + F(int(rng.integers(-16, 17)), 4), p[1] + F(int(rng.integers(-16, 17)), 4))
+        A = corners(x, y, c, s, l, w)
+        want = exact_poly_seg(A, p, q)
+        got = bool(G.obb_segment(f(x), f(y), f(c), f(s), f(l), f(w), f(p[0]), f(p[1]), f(q[0]), f(q[1])))
+        assert got == want, (A, p, q)
+        n += want
+        # disc vs box: exact squared distance from the centre to the box
+        r = F(int(rng.integers(1, 9)), 4)
+        tx, ty = p[0] - x, p[1] - y
+        qx, qy = abs(tx * c + ty * s) - l, abs(ty * c - tx * s) - w
+        dx, dy = max(qx, 0), max(qy, 0)
+        assert bool(G.obb_circle(f(x), f(y), f(c), f(s), f(l), f(w), f(p[0]), f(p[1]), f(r))) == (dx * dx + dy * dy <= r * r)
+        # disc vs segment: exact squared distance
+        ddx, ddy = q[0] - p[0], q[1] - p[1]
+        dd = ddx * ddx + ddy * ddy
+        t = F(0) if dd == 0 else max(F(0), min(F(1), ((x - p[0]) * ddx + (y - p[1]) * ddy) / dd))
+        ex, ey = x - p[0] - t * ddx, y - p[1] - t * ddy
+        assert bool(G.circle_segment(f(x), f(y), f(r), f(p[0]), f(p[1]), f(q[0]), f(q[1]))) == (ex * ex + ey * ey <= r * r)
+    assert 100 < n < 1400
+    assert G.obb_segment(0, 0, 1, 0, 2, 1, 2, -5, 2, 5)            # grazing the front edge
+    assert G.obb_segment(0, 0, 1, 0, 2, 1, -0.5, 0, 0.5, 0)        # wholly inside
+    assert G.obb_segment(0, 0, 1, 0, 2, 1, 2, 1, 3, 2)             # touches one corner
+    assert not G.obb_segment(0, 0, 1, 0, 2, 1, 2.001, 1, 3, 2)
+    assert G.circle_circle(0, 0, 1, 2, 0, 1) and not G.circle_circle(0, 0, 1, 2.0001, 0, 1)
+
+
+def test_out_of_bound_is_not_contains():
+    """box.contains(pose) is closed: a pose touching the boundary from inside is contained (not out)."""
+    b = (-10.0, 10.0, -5.0, 5.0)
+    for (x, y, c, s, l, w), want in [((8, 0, 1, 0, 2, 1), False), ((8.0001, 0, 1, 0, 2, 1), True), ((0, 4, 1, 0, 2, 1), False),
+                                    ((0, 4.5, 0, 1, 2, 1), True), ((-8, 0, 0.6, 0.8, 2, 1), False), ((-9, 0, 0.6, 0.8, 2, 1), True)]:
+        ex, ey = G.extents(c, s, l, w)
+        assert bool(G.out_of_bound(x, y, ex, ey, b)) == want
+        cs = G.obb_corners(x, y, np.arctan2(s, c), l, w)
+        inside = (cs[:, 0] >= b[0]).all() and (cs[:, 0] <= b[1]).all() and (cs[:, 1] >= b[2]).all() and (cs[:, 1] <= b[3]).all()
+        assert inside == (not want) or abs(abs(cs).max() - 10) < 1e-9
+
+
+def test_pose_corner_order_follows_reference_ring():
+    """vehicle.py:133-140: [(+L/2,-W/2), (+L/2,+W/2), (-L/2,+W/2), (-L/2,-W/2)] rotated by the heading."""
+    cs = G.obb_corners(10.0, 5.0, np.pi / 2, 2.142, 0.8995)
+    np.testing.assert_allclose(cs, [[10.8995, 7.142], [9.1005, 7.142], [9.1005, 2.858], [10.8995, 2.858]], atol=1e-12)
