@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt2d_b200.so")
+LIB_PATH = os.environ.get("T2D_B200_LIB", os.path.join(_HERE, "libt2d_b200.so"))   # override: A/B builds of the kernels
 
 
 class T2DError(RuntimeError):
@@ -45,6 +45,7 @@ SYMBOLS = {
     "t2d_check_events": (C.c_int, [_P] + [_P] * 4),
     "t2d_reset": (C.c_int, [_P, _P, _P, C.c_int] + [_P] * 7),
     "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 9),
+    "t2d_debug_set_clock_buffer": (C.c_int, [_P, _P]),
     "t2d_launch_count": (C.c_int64, []),
 }
 

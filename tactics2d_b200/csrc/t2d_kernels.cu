@@ -70,6 +70,7 @@ struct StepArgs {
   int do_physics, has_bounds, vec_ok, needs_vel_in;
   float bxmin, bxmax, bymin, bymax;
   float rb_max;                    // largest bounding radius in the type table (broadphase threshold)
+  long long* dbg_clock;            // optional [n_tiles][8] phase time stamps (T2D_DEBUG_CLOCK); nullptr in production
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -181,7 +182,7 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
   } else if (p.model == MODEL_POINTMASS_EULER) {
     pointmass_euler_step(io, p, n_steps, dt, dt_rem);
   } else {
-    sincosf(io.h, &io.sh, &io.ch);
+    sincos_fast(io.h, &io.sh, &io.ch);
   }
 }
 
@@ -241,6 +242,7 @@ __device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* pos
 }
 
 constexpr int QCAP = 192;   // per-warp candidate queue (pairs); overflow is handled inline
+constexpr int POS_EXT_PER_WARP = 448;   // circularly extended x / y arrays: (32 / G) x (1.5 MP + 8) <= 448 floats per warp
 
 // Exact test of one candidate pair (tile indices ti, tj of the same scenario); a hit is recorded for both
 // ends as the minimum partner index (scenario-local), which is what "first hit in list order" means.
@@ -253,17 +255,47 @@ __device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, const fl
   }
 }
 
-// Broadphase candidates of one partner (tile index tj) against the lane's PPL participants: push them on the
-// warp's queue (bit i of cand: participant t0 + i).  1 <= q - i <= Mh keeps every unordered pair once.
-__device__ __noinline__ void pair_enqueue(unsigned cand, int q, int tj, int t0, int Mh, int mp_shift, const float4* poseA,
-                                          const float4* poseB, int* hitmin, unsigned* queue, int* qcount) {
-  for (int i = 0; i < MAX_PPL; ++i) {
-    if (!((cand >> i) & 1u)) continue;
-    const int k = q - i;
-    if (k < 1 || k > Mh) continue;
+// Broadphase slow path.  `bits` holds the distance-test verdicts of four partner-loop iterations of this lane:
+// bit ((uu * PPL + i) * 2 + e) = own participant m0 + i against extended slot m0 + 2 (u_base + uu) + e.  Keep the
+// combinations whose partner offset q is 1..Mh (every unordered pair once; q <= 0 are the lane's own participants
+// or pairs owned by the other end) and push them on the warp's queue.
+template <int PPL>
+__device__ __forceinline__ void pair_enqueue_bits(unsigned bits, int u_base, int t0, int tb, int m0, int M, int Mh,
+                                                  unsigned* queue, int* qcount) {
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int e = b & 1, i = (b >> 1) & (PPL - 1), uu = (b >> 1) / PPL;   // PPL is a power of two
+    const int u = u_base + uu;
+    const int q = 2 * u + e - i;
+    if (q < 1 || q > Mh) continue;
+    int pj = m0 + 2 * u + e;          // < 2.5 M: at most two wraps
+    if (pj >= M) pj -= M;
+    if (pj >= M) pj -= M;
+    const int tj = tb + pj;
+    // No function call may appear in this loop: a CALL makes the compiler keep only callee-saved registers
+    // live across it and rematerialise everything else in every iteration of the partner loop.  When the
+    // queue is full the count keeps growing; the caller then falls back to the exhaustive pass.
     const int slot = atomicAdd(qcount, 1);
     if (slot < QCAP) queue[slot] = ((unsigned)(t0 + i) << 16) | (unsigned)tj;
-    else pair_resolve(t0 + i, tj, mp_shift, poseA, poseB, hitmin);   // dense scene: resolve in place
+  }
+}
+
+// Dense-scene fallback (the candidate queue overflowed): every lane resolves all pairs of its own participants
+// against all partners of the scenario directly.  Correct for any density, slow, and never on the hot path.
+template <int PPL>
+__device__ __noinline__ void pair_exhaustive(int t0, int tb, int m0, int M, int mp_shift, float rb_max, const float4* poseA,
+                                             const float4* poseB, int* hitmin) {
+  for (int i = 0; i < PPL; ++i) {
+    if (m0 + i >= M) break;
+    const float4 a = poseA[t0 + i];
+    if (!(a.x == a.x)) continue;
+    const float rr = a.z + rb_max;
+    for (int j = m0 + i + 1; j < M; ++j) {
+      const float4 b = poseA[tb + j];
+      const float dx = b.x - a.x, dy = b.y - a.y;
+      if (fmaf(dx, dx, dy * dy) <= fmaf(rr * rr, 1.00001f, 1e-12f)) pair_resolve(t0 + i, tb + j, mp_shift, poseA, poseB, hitmin);
+    }
   }
 }
 
@@ -295,27 +327,26 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
   float4* s_poseB = s_poseA + wpc * POSE_PER_WARP;
   int* s_hit = reinterpret_cast<int*>(s_poseB + wpc * POSE_PER_WARP);
   unsigned* s_queue = reinterpret_cast<unsigned*>(s_hit + wpc * POSE_PER_WARP);
-  int* s_qcount = reinterpret_cast<int*>(s_queue + wpc * QCAP);
+  float* s_posx = reinterpret_cast<float*>(s_queue + wpc * QCAP);
+  float* s_posy = s_posx + wpc * POS_EXT_PER_WARP;
+  int* s_qcount = reinterpret_cast<int*>(s_posy + wpc * POS_EXT_PER_WARP);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_qcount + ((wpc + 3) & ~3));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0 && map_smem_bytes > 0) {
+  // Stage the type table and the map tile with TMA bulk copies (UBLKCP) on one mbarrier; the wait sits after
+  // the first tile's global loads have been issued, so the staging overlaps the cold HBM reads.
+  if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
   }
-  {
-    const int words = A.n_types * (int)(sizeof(Params) / 4);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.table);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s_table);
-    for (int i = tid; i < words; i += (int)blockDim.x) dst[i] = src[i];
-  }
   __syncthreads();
-  if (tid == 0 && map_smem_bytes > 0) {
-    mbar_expect_tx(s_bar, (uint32_t)map_smem_bytes);
-    bulk_g2s(s_map, A.map_blob, (uint32_t)map_smem_bytes, s_bar);
+  if (tid == 0) {
+    mbar_expect_tx(s_bar, (uint32_t)(table_bytes + map_smem_bytes));
+    bulk_g2s(s_table, A.table, (uint32_t)table_bytes, s_bar);
+    if (map_smem_bytes > 0) bulk_g2s(s_map, A.map_blob, (uint32_t)map_smem_bytes, s_bar);
   }
-  bool map_ready = (map_smem_bytes == 0);
+  bool staged = false;
   const unsigned char* mapb = A.map_in_smem ? s_map : A.map_blob;
 
   const int G = A.G, M = A.M;
@@ -333,6 +364,11 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
   const int tb = sub * MP, t0 = tb + m0;
   int mp_shift = 0;
   while ((1 << mp_shift) < MP) ++mp_shift;
+  // circularly extended positions of this scenario: slot k holds participant k mod M, so the partner loop reads
+  // consecutive slots (two per 64-bit load) without wrap-around logic
+  const int EXT = (3 * MP) / 2 + 8;
+  float* posx = s_posx + warp * POS_EXT_PER_WARP + sub * EXT;
+  float* posy = s_posy + warp * POS_EXT_PER_WARP + sub * EXT;
   const int Mh = M >> 1;                // partner offsets 1..Mh cover every unordered pair
 
   const long long n_tiles = ((long long)A.N + spw - 1) / spw;
@@ -343,6 +379,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
     if (nvalid < 0) nvalid = 0;
     const long long idx0 = n * M + m0;
 
+    #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[tile * 8 + (k)] = clock64(); } while (0)
+    T2D_STAMP(0);
     // ------------------------------------------------------------------ load
     float sx[PPL], sy[PPL], shd[PPL], sv[PPL], svx[PPL], svy[PPL], a0[PPL], a1[PPL];
     int tidv[PPL];
@@ -391,6 +429,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
         }
       }
     }
+    if (!staged) {   // table + map tile landed? (first tile only)
+      mbar_wait(s_bar, 0);
+      staged = true;
+    }
     if (A.cfg_flags & T2D_CFG_STEER_FIRST) {
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
@@ -399,6 +441,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
       }
     }
 
+    T2D_STAMP(1);
     // ------------------------------------------------------------------ physics
     float ch[PPL], sh[PPL];
     bool active[PPL];
@@ -445,12 +488,15 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
             sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
             ch[i] = io.ch; sh[i] = io.sh;
           } else {
-            sincosf(shd[i], &sh[i], &ch[i]);   // static participant: the pose only
+            sincos_fast(shd[i], &sh[i], &ch[i]);   // static participant: the pose only
           }
         }
       }
       // ---------------------------------------------------------------- store state
-      if (nvalid == PPL && A.vec_ok) {
+      bool all_active = true;
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) all_active = all_active && active[i];
+      if (nvalid == PPL && A.vec_ok && all_active) {   // (an inactive slot keeps its state: vx, vy may not even be loaded)
         st_vec<float, PPL>(A.x + idx0, sx);
         st_vec<float, PPL>(A.y + idx0, sy);
         st_vec<float, PPL>(A.h + idx0, shd);
@@ -466,9 +512,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < PPL; ++i) sincosf(shd[i], &sh[i], &ch[i]);
+      for (int i = 0; i < PPL; ++i) sincos_fast(shd[i], &sh[i], &ch[i]);
     }
 
+    T2D_STAMP(2);
     // ------------------------------------------------------------------ poses -> shared
     // Only (x, y, bounding radius) stay in registers; the full pose lives in the warp's smem tile.
     float px[PPL], py[PPL], rb[PPL];
@@ -486,10 +533,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
       poseA[t0 + i] = make_float4(px[i], py[i], rb[i], shd[i]);
       poseB[t0 + i] = make_float4(ch[i], sh[i], circle ? p.radius : p.half_len, circle ? -1.0f : p.half_wid);
       hitmin[t0 + i] = 0x7fffffff;
+      if (m0 + i < M)
+        for (int k = m0 + i; k < EXT; k += M) { posx[k] = px[i]; posy[k] = py[i]; }
     }
     if (lane == 0) *qcount = 0;
     __syncwarp();
 
+    T2D_STAMP(3);
     // ------------------------------------------------------------------ dynamic collision
     // Every unordered pair once: participant i tests partners (i+1 .. i+M/2) mod M.  A lane walks the
     // partners of its PPL participants together (one 128-bit pose load per partner, PPL distance tests);
@@ -503,27 +553,48 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
         const float rr = rb[i] + A.rb_max;
         thr[i] = fmaf(rr * rr, 1.00001f, 1e-12f);   // conservative: any partner's bounding radius <= rb_max
       }
-      // hot loop: every lane runs it (idle slots hold NaN and never pass), no divergence; candidates are rare
-      const int q_end = Mh > 0 ? Mh + PPL - 1 : 0;
-      int pj = m0;
-      for (int q = 1; q <= q_end; ++q) {
-        ++pj;
-        pj = (pj >= M) ? pj - M : pj;
-        const float2 pxy = *reinterpret_cast<const float2*>(&poseA[tb + pj]);   // NaN x for a non-solid partner
-        unsigned cand = 0;
+      // hot loop: every lane runs it (idle slots hold NaN and never pass); branch-free; two partners per
+      // iteration in packed fp32 (FADD2 / FMUL2 / FFMA2).  The verdicts of four iterations are collected in one
+      // 32-bit word; a non-zero word (rare) goes to the out-of-line enqueue.
+      float2 nx2[PPL], ny2[PPL];
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) {
-          const float dx = pxy.x - px[i], dy = pxy.y - py[i];
-          if (fmaf(dx, dx, dy * dy) <= thr[i]) cand |= 1u << i;
+      for (int i = 0; i < PPL; ++i) {
+        nx2[i] = make_float2(-px[i], -px[i]);
+        ny2[i] = make_float2(-py[i], -py[i]);
+      }
+      const int U = Mh > 0 ? (Mh + PPL + 1) >> 1 : 0;   // partner pairs: offsets -(PPL-1) .. >= Mh
+      const float2* bx = reinterpret_cast<const float2*>(posx + m0);
+      const float2* by = reinterpret_cast<const float2*>(posy + m0);
+      const int iters_per_word = 16 / PPL;               // 2 * PPL bits per iteration
+      for (int uw = 0; uw * iters_per_word < U; ++uw) {
+        unsigned bits = 0;
+#pragma unroll
+        for (int uu = 0; uu < iters_per_word; ++uu) {
+          const int u = uw * iters_per_word + uu;
+          if (u < U) {
+            const float2 X = bx[u], Y = by[u];
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) {
+              const float2 dx = __fadd2_rn(X, nx2[i]), dy = __fadd2_rn(Y, ny2[i]);
+              const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+              if (d2.x <= thr[i]) bits |= 1u << ((uu * PPL + i) * 2);
+              if (d2.y <= thr[i]) bits |= 2u << ((uu * PPL + i) * 2);
+            }
+          }
         }
-        if (cand) pair_enqueue(cand, q, tb + pj, t0, Mh, mp_shift, poseA, poseB, hitmin, queue, qcount);
+        if (bits) pair_enqueue_bits<PPL>(bits, uw * iters_per_word, t0, tb, m0, M, Mh, queue, qcount);
       }
       __syncwarp();
-      // narrowphase: the queued candidate pairs, one per lane
-      const int n_q = min(*qcount, QCAP);
-      for (int k = lane; k < n_q; k += 32) {
-        const unsigned e = queue[k];
-        pair_resolve((int)(e >> 16), (int)(e & 0xffffu), mp_shift, poseA, poseB, hitmin);
+      T2D_STAMP(4);
+      // narrowphase: the queued candidate pairs, one per lane (or the exhaustive pass if the queue overflowed)
+      const int n_q = *qcount;
+      if (n_q <= QCAP) {
+        for (int k = lane; k < n_q; k += 32) {
+          const unsigned e = queue[k];
+          pair_resolve((int)(e >> 16), (int)(e & 0xffffu), mp_shift, poseA, poseB, hitmin);
+        }
+      } else {
+        pair_exhaustive<PPL>(t0, tb, m0, M, mp_shift, A.rb_max, poseA, poseB, hitmin);
       }
       __syncwarp();
 #pragma unroll
@@ -533,21 +604,19 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
       }
     }
 
+    T2D_STAMP(5);
     // ------------------------------------------------------------------ static collision
     int hseg[PPL];
 #pragma unroll
     for (int i = 0; i < PPL; ++i) hseg[i] = -1;
     if (mapb != nullptr) {
-      if (!map_ready) {
-        mbar_wait(s_bar, 0);
-        map_ready = true;
-      }
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
         if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], mapb, A.map_fine))
           hseg[i] = static_slow(poseA, poseB, t0 + i, rb[i], mapb);
     }
 
+    T2D_STAMP(6);
     // ------------------------------------------------------------------ out of bound + flags
     uint8_t fl[PPL];
 #pragma unroll
@@ -601,9 +670,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
         if (A.done) A.done[n] = st != T2D_STATUS_NORMAL;             // parking.py:243-248
       }
     }
+    T2D_STAMP(7);
     __syncwarp();   // pose tile is reused by the next tile
   }
-  if (!map_ready) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
+  if (!staged) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
 }
 
 // ---------------------------------------------------------------------------- K2
@@ -703,6 +773,7 @@ struct t2d_ctx {
   int max_smem_optin = 0;
   int configured_smem = -1;
   float rb_max = 0.0f;
+  long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
   int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -735,12 +806,12 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   c->device = device;
   c->N = n_scenarios;
   c->M = m_participants;
-  // participants per lane: the smallest of 1 / 2 / 4 that lets one warp span a scenario (more warps in
-  // flight for the same batch), overridable with T2D_PPL for experiments
-  int ppl = m_participants <= 32 ? 1 : (m_participants <= 64 ? 2 : 4);
+  // participants per lane: 4 (measured on B200 at 4096 x 64: 28.6 us vs 37.1 us with 2 - the partner loop and
+  // the per-thread set-up amortise over more participants); T2D_PPL overrides for experiments
+  int ppl = 4;
   if (const char* e = getenv("T2D_PPL")) {
     const int v = atoi(e);
-    if ((v == 1 || v == 2 || v == 4) && 32 * v >= m_participants) ppl = v;
+    if ((v == 2 || v == 4) && 32 * v >= m_participants) ppl = v;   // the packed partner loop needs an even lane base
   }
   c->ppl = ppl;
   int g = 1;
@@ -980,6 +1051,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.vec_ok = vec ? 1 : 0;
 
   A.rb_max = c->rb_max;
+  A.dbg_clock = c->dbg_clock;
   const int table_bytes = ((c->n_types * (int)sizeof(Params) + 15) / 16) * 16;
   const int spw = 32 / c->G;
   const long long tiles = ((long long)c->N + spw - 1) / spw;
@@ -990,14 +1062,14 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
     if ((tiles + w - 1) / w >= 6LL * c->sm_count) { wpc = w; break; }
   }
   const int smem_fixed = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 16;
-  const int smem = smem_fixed + wpc * (POSE_PER_WARP * (2 * (int)sizeof(float4) + (int)sizeof(int)) + QCAP * 4) + 32;
+  const int smem = smem_fixed + wpc * (POSE_PER_WARP * (2 * (int)sizeof(float4) + (int)sizeof(int)) + QCAP * 4 + 2 * POS_EXT_PER_WARP * 4) + 32;
   if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");
   using kernel_t = void (*)(StepArgs);
   kernel_t kern;
   if (c->kin_only)
-    kern = c->ppl == 1 ? (kernel_t)t2d_step_kernel<1, true> : (c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, true> : (kernel_t)t2d_step_kernel<4, true>);
+    kern = c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, true> : (kernel_t)t2d_step_kernel<4, true>;
   else
-    kern = c->ppl == 1 ? (kernel_t)t2d_step_kernel<1, false> : (c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, false> : (kernel_t)t2d_step_kernel<4, false>);
+    kern = c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, false> : (kernel_t)t2d_step_kernel<4, false>;
   if (smem > c->configured_smem) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->configured_smem = smem;
@@ -1014,6 +1086,12 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   kern<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+int t2d_debug_set_clock_buffer(t2d_ctx* c, long long* device_buffer) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  c->dbg_clock = device_buffer;
   return T2D_OK;
 }
 

@@ -74,11 +74,49 @@ T2D_HD float wrap_two_pi(float phi) {
   return r;
 }
 
-// (cos, sin) of a small angle d, |d| <= 0.25: Taylor, abs error < 2e-9 / 1.3e-8 relative.
-T2D_HD void small_sincos(float d, float& sn, float& hv /* 1 - cos */) {
-  float d2 = d * d;
-  sn = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -1.6666667e-1f), 1.0f);
-  hv = d2 * fmaf(d2, fmaf(d2, 1.3888889e-3f, -4.1666667e-2f), 0.5f);
+// sincos without the library's large-argument (Payne-Hanek) path inlined at every call site: Cody-Waite
+// reduction to [-pi/4, pi/4] (three-term pi/2, exact for |x| <= 512) + degree-7/8 polynomials; abs error < 1e-7.
+// Larger arguments go to one out-of-line copy of the library routine.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__ void sincosf_slow(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+#else
+inline void sincosf_slow(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+#endif
+
+T2D_HD void sincos_fast(float x, float* sn, float* cs) {
+  if (!(fabsf(x) <= 512.0f)) {
+    sincosf_slow(x, sn, cs);
+    return;
+  }
+  const float k = rintf(x * 0.636619772f);
+  float r = fmaf(-k, 1.570556640625f, x);
+  r = fmaf(-k, 2.396702766418457e-4f, r);
+  r = fmaf(-k, 1.5893254712295857e-8f, r);
+  const float z = r * r;
+  const float s = fmaf(r * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+  const float c = fmaf(z * z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                       fmaf(-0.5f, z, 1.0f));
+  const int q = (int)k;
+  const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+  *sn = (q & 2) ? -a : a;
+  *cs = ((q + 1) & 2) ? -b : b;
+}
+
+// Small-angle rotation, |d| <= 0.25 (Taylor: |err| < 2e-9 on cos, 1.3e-8 relative on sin).
+constexpr float SIN_C3 = -1.6666667e-1f, SIN_C5 = 8.3333333e-3f;
+constexpr float COS_C2 = -0.5f, COS_C4 = 4.1666667e-2f, COS_C6 = -1.3888889e-3f;
+
+// (c, s) <- (c, s) rotated by d, given d and nd = -d.  Written as the exact operation sequence the packed
+// (FFMA2) kernel path uses, so that the scalar and packed paths are bit-identical.
+T2D_HD void rotate_small(float& c, float& s, float d, float nd) {
+  const float dd = d * d;
+  const float ts = fmaf(dd, fmaf(dd, SIN_C5, SIN_C3), 1.0f);
+  const float sn = d * ts, nsn = nd * ts;
+  const float nhv = dd * fmaf(dd, fmaf(dd, COS_C6, COS_C4), COS_C2);   // cos(d) - 1
+  const float cn = fmaf(s, nsn, fmaf(c, nhv, c));
+  const float sm = fmaf(c, sn, fmaf(s, nhv, s));
+  c = cn;
+  s = sm;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -110,7 +148,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     io.steer[i] = d;
     float L = p[i]->lf + p[i]->lr;                                  // :85
     float sd, cd;
-    sincosf(d, &sd, &cd);
+    sincos_fast(d, &sd, &cd);
     float tan_d = sd / cd;
     float tb = p[i]->lr / L * tan_d;          // tan(beta), beta = atan(lr/L tan delta)  :127
     float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
@@ -119,7 +157,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     kdt[i] = k[i] * dt;
     adt[i] = a[i] * dt;
     float sp, cp;
-    sincosf(io.h[i], &sp, &cp);
+    sincos_fast(io.h[i], &sp, &cp);
     c[i] = cp * cb - sp * sb;                    // cos(phi + beta)
     s[i] = sp * cb + cp * sb;                    // sin(phi + beta)
     vlo[i] = p[i]->speed_lo;
@@ -134,7 +172,62 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
 #pragma unroll
   for (int i = 0; i < W; ++i) v[i] = io.v[i];
   // main sub-steps :137-148 ; derivatives from the OLD (phi, v), then v clipped
-  if (small) {
+  bool looped = false;
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  // Blackwell packed fp32: two participants per FFMA2 / FMUL2 / FADD2 (SASS FFMA2 ...), the same operation
+  // sequence as rotate_small() lane by lane, so the results are bit-identical to the scalar path.
+  if constexpr (W == 4) {
+    if (small) {
+      float2 C2[2], S2[2], V2[2], SX2[2], SY2[2], SV2[2], KDT2[2], NKDT2[2], ADT2[2], W12[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        C2[q] = make_float2(c[2 * q], c[2 * q + 1]);
+        S2[q] = make_float2(s[2 * q], s[2 * q + 1]);
+        V2[q] = make_float2(v[2 * q], v[2 * q + 1]);
+        SX2[q] = make_float2(0.0f, 0.0f); SY2[q] = SX2[q]; SV2[q] = SX2[q];
+        KDT2[q] = make_float2(kdt[2 * q], kdt[2 * q + 1]);
+        NKDT2[q] = make_float2(-kdt[2 * q], -kdt[2 * q + 1]);
+        ADT2[q] = make_float2(adt[2 * q], adt[2 * q + 1]);
+        W12[q] = make_float2(w1[2 * q], w1[2 * q + 1]);
+      }
+      const float2 K_S5 = make_float2(SIN_C5, SIN_C5), K_S3 = make_float2(SIN_C3, SIN_C3), K_ONE = make_float2(1.0f, 1.0f);
+      const float2 K_C6 = make_float2(COS_C6, COS_C6), K_C4 = make_float2(COS_C4, COS_C4), K_C2 = make_float2(COS_C2, COS_C2);
+      float fi = -1.0f;
+      for (int it = 0; it < n_steps; ++it) {
+        fi += 1.0f;
+        const float2 FI = make_float2(fi, fi);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          SX2[q] = __ffma2_rn(V2[q], C2[q], SX2[q]);
+          SY2[q] = __ffma2_rn(V2[q], S2[q], SY2[q]);
+          SV2[q] = __fadd2_rn(SV2[q], V2[q]);
+          const float2 d = __fmul2_rn(KDT2[q], V2[q]), nd = __fmul2_rn(NKDT2[q], V2[q]);
+          const float2 dd = __fmul2_rn(d, d);
+          const float2 ts = __ffma2_rn(dd, __ffma2_rn(dd, K_S5, K_S3), K_ONE);
+          const float2 sn = __fmul2_rn(d, ts), nsn = __fmul2_rn(nd, ts);
+          const float2 nhv = __fmul2_rn(dd, __ffma2_rn(dd, __ffma2_rn(dd, K_C6, K_C4), K_C2));
+          const float2 cn = __ffma2_rn(S2[q], nsn, __ffma2_rn(C2[q], nhv, C2[q]));
+          const float2 sm = __ffma2_rn(C2[q], sn, __ffma2_rn(S2[q], nhv, S2[q]));
+          C2[q] = cn;
+          S2[q] = sm;
+          const float2 wn = __ffma2_rn(FI, ADT2[q], W12[q]);
+          V2[q].x = clampf(wn.x, vlo[2 * q], vhi[2 * q]);
+          V2[q].y = clampf(wn.y, vlo[2 * q + 1], vhi[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        c[2 * q] = C2[q].x; c[2 * q + 1] = C2[q].y; s[2 * q] = S2[q].x; s[2 * q + 1] = S2[q].y;
+        v[2 * q] = V2[q].x; v[2 * q + 1] = V2[q].y;
+        Sx[2 * q] = SX2[q].x; Sx[2 * q + 1] = SX2[q].y; Sy[2 * q] = SY2[q].x; Sy[2 * q + 1] = SY2[q].y;
+        Sv[2 * q] = SV2[q].x; Sv[2 * q + 1] = SV2[q].y;
+      }
+      looped = true;
+    }
+  }
+#endif
+  if (looped) {
+  } else if (small) {
     float fi = -1.0f;
     for (int it = 0; it < n_steps; ++it) {
       fi += 1.0f;
@@ -143,13 +236,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
         Sx[i] = fmaf(v[i], c[i], Sx[i]);
         Sy[i] = fmaf(v[i], s[i], Sy[i]);
         Sv[i] += v[i];
-        const float d = kdt[i] * v[i];
-        float sn, hv;
-        small_sincos(d, sn, hv);
-        const float c2 = c[i] - fmaf(c[i], hv, s[i] * sn);
-        const float s2 = s[i] - fmaf(s[i], hv, -c[i] * sn);
-        c[i] = c2;
-        s[i] = s2;
+        rotate_small(c[i], s[i], kdt[i] * v[i], -kdt[i] * v[i]);
         v[i] = clampf(fmaf(fi, adt[i], w1[i]), vlo[i], vhi[i]);   // w_{it+1}
       }
     }
@@ -163,7 +250,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
         Sy[i] = fmaf(v[i], s[i], Sy[i]);
         Sv[i] += v[i];
         float sn, cs;
-        sincosf(kdt[i] * v[i], &sn, &cs);
+        sincos_fast(kdt[i] * v[i], &sn, &cs);
         const float c2 = c[i] * cs - s[i] * sn;
         const float s2 = s[i] * cs + c[i] * sn;
         c[i] = c2;
@@ -185,7 +272,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     }
     float hn = wrap_two_pi(io.h[i] + dphi);     // np.mod(phi, 2 pi)                        :169
     float sh, ch;
-    sincosf(hn, &sh, &ch);
+    sincos_fast(hn, &sh, &ch);
     io.x[i] = x; io.y[i] = y; io.h[i] = hn; io.v[i] = v[i];
     io.vx[i] = v[i] * ch;                        // v cos(phi), no beta                    :170
     io.vy[i] = v[i] * sh;                        //                                        :171
@@ -248,7 +335,7 @@ T2D_HD void dynamics_step(OneIO& io, const Params& p, int n_steps, double dt) {
   float hn = (float)hd;
   if (hn >= TWO_PI_HI) hn = 0.0f;
   float sh, ch;
-  sincosf(hn, &sh, &ch);
+  sincos_fast(hn, &sh, &ch);
   io.x = (float)x; io.y = (float)y; io.h = hn; io.v = (float)v;
   io.vx = io.v * ch; io.vy = io.v * sh;      // State.velocity of a State without vx, vy (state.py:160-165)
   io.ch = ch; io.sh = sh;
@@ -294,7 +381,7 @@ T2D_HD void pointmass_newton_step(OneIO& io, const Params& p, double dt) {
   io.vx = (float)ovx; io.vy = (float)ovy;
   io.h = (float)atan2(ovy, ovx);
   io.v = (float)sqrt(ovx * ovx + ovy * ovy);               // State.speed (state.py:143-146)
-  sincosf(io.h, &io.sh, &io.ch);
+  sincos_fast(io.h, &io.sh, &io.ch);
 }
 
 T2D_HD void pointmass_euler_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem) {
@@ -319,7 +406,7 @@ T2D_HD void pointmass_euler_step(OneIO& io, const Params& p, int n_steps, double
   io.x = (float)x; io.y = (float)y; io.h = (float)heading;
   io.vx = (float)vx; io.vy = (float)vy;
   io.v = (float)sqrt(vx * vx + vy * vy);
-  sincosf(io.h, &io.sh, &io.ch);
+  sincos_fast(io.h, &io.sh, &io.ch);
 }
 
 // ==========================================================================================

@@ -105,7 +105,7 @@ def config2(n: int = 4096, m: int = 64, seed: int = 1, size: float = 200.0, jitt
     """C2: N x M SingleTrackKinematics vehicles (types sampled from the 9 VEHICLE_TEMPLATE rows) in a
     200 m arena with the synthetic grid map; jitter tuned for a few percent of colliding participants."""
     rng = np.random.default_rng(seed)
-    table = TypeTable.from_templates("kinematics")
+    table = TypeTable.vehicles("kinematics")   # the 9 VEHICLE_TEMPLATE rows: a kinematics-only table
     x, y, h, v, tid = _arena(rng, n, m, size, jitter, 15.0, table, list(range(9)))
     return _finish(table, x, y, h, v, tid, grid_wall_segments(size), (-8.0, size + 8.0, -8.0, size + 8.0),
                    f"C2 {n}x{m} kinematics + OBB collision, synthetic grid map")
@@ -151,7 +151,7 @@ def config4(n: int = 16384, m: int = 32, seed: int = 4, segments=None, bounds=No
 def config5(n: int = 65536, m: int = 128, seed: int = 5, segments=None, bounds=None, size: float = 280.0) -> Scene:
     """C5: broadphase stress - N x 128 kinematic vehicles, rounD-like map."""
     rng = np.random.default_rng(seed)
-    table = TypeTable.from_templates("kinematics")
+    table = TypeTable.vehicles("kinematics")
     x, y, h, v, tid = _arena(rng, n, m, size, None, 15.0, table, list(range(9)))
     if bounds is None:
         bounds = (-8.0, size + 8.0, -8.0, size + 8.0)

@@ -166,6 +166,13 @@ class TypeTable:
         return out
 
     @classmethod
+    def vehicles(cls, vehicle_model: str = "kinematics") -> "TypeTable":
+        """The 9 vehicle templates only (a table without point-mass rows lets the kinematics-only kernel run)."""
+        from .participant.element.participant_template import VEHICLE_TEMPLATE
+
+        return cls([TypeParams.vehicle(k, vehicle_model) for k in VEHICLE_TEMPLATE])
+
+    @classmethod
     def from_templates(cls, vehicle_model: str = "kinematics", pedestrian_backend: str = "newton") -> "TypeTable":
         """All 16 template types: 9 vehicles, 3 cyclists, 4 pedestrians (participant_template.py:42-257)."""
         from .participant.element.participant_template import (CYCLIST_TEMPLATE, PEDESTRIAN_TEMPLATE,

@@ -13,6 +13,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The CUDA library is built in-tree (git-ignored): build it when it is missing or stale so that a fresh
+    checkout can run the suite (nvcc cross-compiles sm_100a without a GPU)."""
+    import shutil
+
+    if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+        import __graft_entry__ as entry
+
+        try:
+            entry.build()
+        except Exception as e:  # the ABI test then reports the missing library
+            print(f"[conftest] build() failed: {e}")
+
+
 @pytest.fixture(scope="session")
 def hostsim():
     """g++ build of the device arithmetic header (tests/hostsim/hostsim.cpp) - test harness only."""
