@@ -159,8 +159,8 @@ int t2d_physics_step(int device, const t2d_type_params* params /*host*/, int int
                      float* x, float* y, float* heading, float* speed, float* vx, float* vy, const float* action,
                      float* applied, void* stream);
 
-/* Diagnostics: device buffer int64[ceil(N / scenarios_per_warp)][8] that receives clock64() at the eight phase
- * boundaries of every warp tile of t2d_step (load, physics, pose, pair loop, pair drain, static, out-of-bound, end);
+/* Diagnostics: device buffer int64[ceil(N / scenarios_per_warp)][10] that receives clock64() at the eight phase
+ * boundaries of every warp tile of t2d_step (load, physics, pose, pair loop, pair drain, static, out-of-bound, end), the SM id and the warp's kernel-entry clock;
  * NULL (default) disables it.  Used by profiles/phase_clocks.py. */
 int t2d_debug_set_clock_buffer(t2d_ctx* ctx, long long* device_buffer);
 

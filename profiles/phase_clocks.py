@@ -21,7 +21,7 @@ act = torch.from_numpy(synthetic.random_actions(3, (n, m))).cuda()
 for _ in range(3):
     w.step(act)
 tiles = n  # upper bound on warp tiles
-buf = torch.zeros((tiles, 8), dtype=torch.int64, device="cuda")
+buf = torch.zeros((tiles, 10), dtype=torch.int64, device="cuda")
 _lib.check(w.lib.t2d_debug_set_clock_buffer(w._ctx, C.c_void_p(buf.data_ptr())))
 torch.cuda.synchronize()
 w.step(act)
@@ -30,7 +30,19 @@ b = buf.cpu().numpy()
 b = b[b[:, 0] != 0]
 t0 = b[:, 0].min()
 names = ["load", "physics", "pose", "pair loop", "pair drain", "static", "oob+status"]
+smid, entry = b[:, 8], b[:, 9]
+b = b[:, :8]
 d = np.diff(b, axis=1)
+# per-SM view (clock64 is per SM): when do warps enter the kernel, and how long is an SM busy?
+spans, ramps, counts = [], [], []
+for sm in np.unique(smid):
+    sel = smid == sm
+    e0 = entry[sel].min()
+    spans.append(b[sel, 7].max() - e0)
+    ramps.append(entry[sel].max() - e0)
+    counts.append(sel.sum())
+print(f"per SM: tiles {np.mean(counts):.1f} (min {np.min(counts)}, max {np.max(counts)}); busy span mean {np.mean(spans):.0f} max {np.max(spans)}; "
+      f"last warp enters {np.mean(ramps):.0f} cycles after the first (max {np.max(ramps)}); prologue (entry -> first stamp) mean {np.mean(b[:, 0] - entry):.0f}")
 print(f"{len(b)} warp tiles; kernel span {b[:, 7].max() - t0} cycles (SM clock, per-SM counters: spans across SMs are approximate)")
 print(f"tile start (rel. first): mean {np.mean(b[:, 0] - t0):.0f}  p50 {np.percentile(b[:, 0] - t0, 50):.0f}  max {np.max(b[:, 0] - t0)}")
 print(f"tile lifetime: mean {np.mean(b[:, 7] - b[:, 0]):.0f}  p95 {np.percentile(b[:, 7] - b[:, 0], 95):.0f}")

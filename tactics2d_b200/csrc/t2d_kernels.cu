@@ -59,6 +59,7 @@ struct StepArgs {
   uint8_t* done;
   const unsigned char* map_blob;   // device; nullptr when no segments
   const uint8_t* map_fine;         // device; fine clearance field (bytes), read through L1/L2
+  MapHeader mh;                    // copy of the blob header (grid geometry, section offsets): constant bank
   const Params* table;             // device
   int map_bytes, map_in_smem;
   int n_types;
@@ -188,48 +189,19 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
 
 // Static broadphase, level 1: the clearance field.  One shared-memory load tells whether the pose's
 // bounding circle can reach any segment at all (most participants are nowhere near a wall).
-__device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const unsigned char* mapb,
+__device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const MapHeader& mh,
                                               const uint8_t* fine) {
-  const MapHeader* mh = reinterpret_cast<const MapHeader*>(mapb);
   const float r = rbound * 1.0001f + 1e-3f;
-  const float fx = (ax - mh->x0) * mh->inv_cell, fy = (ay - mh->y0) * mh->inv_cell;
-  const int gx = mh->gx, gy = mh->gy;
+  const float fx = (ax - mh.x0) * mh.inv_cell, fy = (ay - mh.y0) * mh.inv_cell;
+  const int gx = mh.gx, gy = mh.gy;
   if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)gx && fy < (float)gy)) {
     // outside the grid: reachable only within r of its box
     const float ox = fmaxf(fmaxf(-fx, fx - (float)gx), 0.0f), oy = fmaxf(fmaxf(-fy, fy - (float)gy), 0.0f);
-    return fmaxf(ox, oy) * mh->cell <= r;
+    return fmaxf(ox, oy) * mh.cell <= r;
   }
-  const int k = mh->fine;
+  const int k = mh.fine;
   const int ix = min((int)(fx * (float)k), gx * k - 1), iy = min((int)(fy * (float)k), gy * k - 1);
   return (float)__ldg(fine + (size_t)iy * (gx * k) + ix) * CLEAR_QUANT <= r;
-}
-
-// Level 2: first (lowest-index) map segment the pose touches, or -1.  Uniform grid over the map tile:
-// only the cells under the pose's bounding circle are visited.
-__device__ __forceinline__ int static_first_hit(const Pose a, const float rbound, const unsigned char* mapb) {
-  const MapHeader* mh = reinterpret_cast<const MapHeader*>(mapb);
-  const float4* seg = reinterpret_cast<const float4*>(mapb + mh->off_seg);
-  const uint32_t* cell_start = reinterpret_cast<const uint32_t*>(mapb + mh->off_cell);
-  const uint16_t* items = reinterpret_cast<const uint16_t*>(mapb + mh->off_items);
-  const int gx = mh->gx, gy = mh->gy;
-  const float x0 = mh->x0, y0 = mh->y0, inv = mh->inv_cell;
-  const float r = rbound * 1.0001f + 1e-3f;
-  int cx0 = (int)floorf((a.x - r - x0) * inv), cx1 = (int)floorf((a.x + r - x0) * inv);
-  int cy0 = (int)floorf((a.y - r - y0) * inv), cy1 = (int)floorf((a.y + r - y0) * inv);
-  cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, gx - 1); cy1 = min(cy1, gy - 1);
-  int best = 0x7fffffff;
-  for (int cy = cy0; cy <= cy1; ++cy) {
-    for (int cx = cx0; cx <= cx1; ++cx) {
-      const int cidx = cy * gx + cx;
-      const uint32_t b = cell_start[cidx], e = cell_start[cidx + 1];
-      for (uint32_t k = b; k < e; ++k) {
-        const int sidx = items[k];
-        if (sidx >= best) break;   // lists are ascending: nothing better left in this cell
-        if (seg_hit(a, seg[sidx])) best = sidx;
-      }
-    }
-  }
-  return best == 0x7fffffff ? -1 : best;
 }
 
 // Own pose of participant `idx` back from the warp's shared-memory tile (the hot loops keep only x, y
@@ -241,7 +213,7 @@ __device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* pos
   return p;
 }
 
-constexpr int QCAP = 192;   // per-warp candidate queue (pairs); overflow is handled inline
+constexpr int QCAP = 192;   // per-warp queue: candidate pairs, then static participants (0..127) + undecided segments (128..191)
 constexpr int POS_EXT_PER_WARP = 448;   // circularly extended x / y arrays: (32 / G) x (1.5 MP + 8) <= 448 floats per warp
 
 // Exact test of one candidate pair (tile indices ti, tj of the same scenario); a hit is recorded for both
@@ -299,8 +271,101 @@ __device__ __noinline__ void pair_exhaustive(int t0, int tb, int m0, int M, int 
   }
 }
 
-__device__ __noinline__ int static_slow(const float4* poseA, const float4* poseB, int idx, float rbound, const unsigned char* mapb) {
-  return static_first_hit(load_pose(poseA, poseB, idx), rbound, mapb);
+// Static level 2 for ONE participant (tile index ti), run by one lane: walk the grid cells under the bounding
+// circle, fp32-filtered segment test per listed segment, keep the lowest hit.  No function call in here (see
+// pair_enqueue_bits): a segment the filter cannot decide is pushed on the exact queue (entries QX0 .. QCAP-1
+// of the warp's queue, counter qcount) and decided after the loop; if that queue is full the participant is
+// marked (returns -2) for the out-of-line exact walk.
+constexpr int QX0 = 128;   // first exact-queue entry (entries below hold the compacted participant list)
+
+template <typename SegPtr, typename CellPtr, typename ItemPtr>
+__device__ __forceinline__ int static_walk(int ti, const Pose& a, float rbound, const MapHeader& mh, SegPtr seg, CellPtr cell_start,
+                                           ItemPtr items, unsigned* queue, int* qcount) {
+  const int gx = mh.gx, gy = mh.gy;
+  const float x0 = mh.x0, y0 = mh.y0, inv = mh.inv_cell;
+  const float r = rbound * 1.0001f + 1e-3f;
+  int cx0 = (int)floorf((a.x - r - x0) * inv), cx1 = (int)floorf((a.x + r - x0) * inv);
+  int cy0 = (int)floorf((a.y - r - y0) * inv), cy1 = (int)floorf((a.y + r - y0) * inv);
+  cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, gx - 1); cy1 = min(cy1, gy - 1);
+  int best = 0x7fffffff;
+  bool overflow = false;
+  for (int cy = cy0; cy <= cy1; ++cy)
+    for (int cx = cx0; cx <= cx1; ++cx) {
+      const int cidx = cy * gx + cx;
+      const uint32_t b = cell_start[cidx], e = cell_start[cidx + 1];
+      for (uint32_t k = b; k < e; ++k) {
+        const int sidx = items[k];
+        if (sidx >= best) break;   // lists are ascending: nothing better left in this cell
+        const float4 sg = seg[sidx];
+        const int rr = a.w < 0.0f ? circle_segment_f32(a.x, a.y, a.l, sg.x, sg.y, sg.z, sg.w)
+                                  : obb_segment_f32(a.x, a.y, a.c, a.s, a.l, a.w, sg.x, sg.y, sg.z, sg.w);
+        if (rr > 0) {
+          best = sidx;
+        } else if (rr < 0) {
+          const int slot = atomicAdd(qcount, 1);
+          if (slot < QCAP - QX0) queue[QX0 + slot] = ((unsigned)ti << 16) | (unsigned)sidx;
+          else overflow = true;
+        }
+      }
+    }
+  return overflow ? -2 : best;
+}
+
+// Out-of-line exact walk for a participant whose undecided segments did not fit the exact queue (never on the
+// hot path): the same cells, every test through the fp32 filter + fp64 fallback.
+template <typename SegPtr, typename CellPtr, typename ItemPtr>
+__device__ __noinline__ int static_walk_exact(const Pose a, float rbound, const MapHeader mh, SegPtr seg, CellPtr cell_start, ItemPtr items) {
+  const float r = rbound * 1.0001f + 1e-3f;
+  int cx0 = max((int)floorf((a.x - r - mh.x0) * mh.inv_cell), 0), cx1 = min((int)floorf((a.x + r - mh.x0) * mh.inv_cell), mh.gx - 1);
+  int cy0 = max((int)floorf((a.y - r - mh.y0) * mh.inv_cell), 0), cy1 = min((int)floorf((a.y + r - mh.y0) * mh.inv_cell), mh.gy - 1);
+  int best = 0x7fffffff;
+  for (int cy = cy0; cy <= cy1; ++cy)
+    for (int cx = cx0; cx <= cx1; ++cx) {
+      const int cidx = cy * mh.gx + cx;
+      for (uint32_t k = cell_start[cidx]; k < cell_start[cidx + 1]; ++k) {
+        const int sidx = items[k];
+        if (sidx >= best) break;
+        if (seg_hit(a, seg[sidx])) best = sidx;
+      }
+    }
+  return best;
+}
+
+// The static phase of one warp tile.  (1) every lane decides with the clearance field which of its participants
+// can reach a wall at all; (2) those participants are compacted into a list with warp ballots; (3) the list is
+// processed one participant per lane (static_walk), so the divergent cell walks of ~15 % of the participants run
+// side by side instead of one after the other; (4) the few filter-undecided segments are settled in fp64.
+template <int PPL, typename SegPtr, typename CellPtr, typename ItemPtr>
+__device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lane, const MapHeader& mh, SegPtr seg, CellPtr cell_start,
+                                             ItemPtr items, const float4* poseA, const float4* poseB, int* segmin, unsigned* queue,
+                                             int* qcount) {
+  int base = 0;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const bool near = (near_bits >> i) & 1u;
+    const unsigned m = __ballot_sync(0xffffffffu, near);
+    if (near) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)(t0 + i);
+    base += __popc(m);
+  }
+  __syncwarp();
+  for (int k = lane; k < base; k += 32) {
+    const int ti = (int)queue[k];
+    const Pose a = load_pose(poseA, poseB, ti);
+    const int best = static_walk(ti, a, poseA[ti].z, mh, seg, cell_start, items, queue, qcount);
+    segmin[ti] = best;   // one lane per participant: plain store (-2 = needs the exact walk)
+  }
+  __syncwarp();
+  const int n_x = min(*qcount, QCAP - QX0);
+  for (int k = lane; k < n_x; k += 32) {   // undecided (participant, segment) pairs: exact test
+    const unsigned e = queue[QX0 + k];
+    const int ti = (int)(e >> 16), sidx = (int)(e & 0xffffu);
+    if (segmin[ti] != -2 && sidx < segmin[ti] && seg_exact(load_pose(poseA, poseB, ti), seg[sidx])) atomicMin(&segmin[ti], sidx);
+  }
+  for (int k = lane; k < base; k += 32) {   // exact-queue overflow (pathological): redo those participants out of line
+    const int ti = (int)queue[k];
+    if (segmin[ti] == -2) segmin[ti] = static_walk_exact(load_pose(poseA, poseB, ti), poseA[ti].z, mh, seg, cell_start, items);
+  }
+  __syncwarp();
 }
 
 __device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, int idx, float xmin, float xmax, float ymin,
@@ -315,7 +380,7 @@ __device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, 
 // KIN_ONLY: every type in the table is SingleTrackKinematics or static - the fp64 models are compiled out
 // (their register footprint would otherwise bound the occupancy of the whole kernel).
 template <int PPL, bool KIN_ONLY>
-__global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4))) t2d_step_kernel(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   // carve: [map blob | 16B aligned] [type table] [pose tiles] [mbarrier]
   const int map_smem_bytes = A.map_in_smem ? A.map_bytes : 0;
@@ -333,6 +398,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_qcount + ((wpc + 3) & ~3));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t_entry = A.dbg_clock ? clock64() : 0;
 
   // Stage the type table and the map tile with TMA bulk copies (UBLKCP) on one mbarrier; the wait sits after
   // the first tile's global loads have been issued, so the staging overlaps the cold HBM reads.
@@ -347,7 +413,6 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
     if (map_smem_bytes > 0) bulk_g2s(s_map, A.map_blob, (uint32_t)map_smem_bytes, s_bar);
   }
   bool staged = false;
-  const unsigned char* mapb = A.map_in_smem ? s_map : A.map_blob;
 
   const int G = A.G, M = A.M;
   const int spw = 32 / G;               // scenarios per warp
@@ -379,7 +444,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
     if (nvalid < 0) nvalid = 0;
     const long long idx0 = n * M + m0;
 
-    #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[tile * 8 + (k)] = clock64(); } while (0)
+    #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[tile * 10 + (k)] = clock64(); } while (0)
     T2D_STAMP(0);
     // ------------------------------------------------------------------ load
     float sx[PPL], sy[PPL], shd[PPL], sv[PPL], svx[PPL], svy[PPL], a0[PPL], a1[PPL];
@@ -601,7 +666,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
       for (int i = 0; i < PPL; ++i) {
         const int h = hitmin[t0 + i];
         hit[i] = (h == 0x7fffffff) ? -1 : h;
+        hitmin[t0 + i] = 0x7fffffff;   // reused below as the per-participant first-hit segment
       }
+      if (lane == 0) *qcount = 0;
+      __syncwarp();
     }
 
     T2D_STAMP(5);
@@ -609,11 +677,26 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
     int hseg[PPL];
 #pragma unroll
     for (int i = 0; i < PPL; ++i) hseg[i] = -1;
-    if (mapb != nullptr) {
+    if (A.map_blob != nullptr) {
+      unsigned near_bits = 0;
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
-        if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], mapb, A.map_fine))
-          hseg[i] = static_slow(poseA, poseB, t0 + i, rb[i], mapb);
+        if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], A.mh, A.map_fine)) near_bits |= 1u << i;
+      if (__any_sync(0xffffffffu, near_bits != 0)) {
+        if (A.map_in_smem)
+          static_phase<PPL>(near_bits, t0, lane, A.mh, reinterpret_cast<const float4*>(s_map + A.mh.off_seg),
+                            reinterpret_cast<const uint32_t*>(s_map + A.mh.off_cell),
+                            reinterpret_cast<const uint16_t*>(s_map + A.mh.off_items), poseA, poseB, hitmin, queue, qcount);
+        else
+          static_phase<PPL>(near_bits, t0, lane, A.mh, reinterpret_cast<const float4*>(A.map_blob + A.mh.off_seg),
+                            reinterpret_cast<const uint32_t*>(A.map_blob + A.mh.off_cell),
+                            reinterpret_cast<const uint16_t*>(A.map_blob + A.mh.off_items), poseA, poseB, hitmin, queue, qcount);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const int h = hitmin[t0 + i];
+          hseg[i] = (h == 0x7fffffff) ? -1 : h;
+        }
+      }
     }
 
     T2D_STAMP(6);
@@ -671,6 +754,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : (PPL == 2 ? 3 : 4
       }
     }
     T2D_STAMP(7);
+    if (A.dbg_clock && lane == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      A.dbg_clock[tile * 10 + 8] = smid;
+      A.dbg_clock[tile * 10 + 9] = t_entry;
+    }
     __syncwarp();   // pose tile is reused by the next tile
   }
   if (!staged) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
@@ -763,6 +852,7 @@ struct t2d_ctx {
   Params* d_table = nullptr;
   unsigned char* d_map = nullptr;
   uint8_t* d_fine = nullptr;
+  MapHeader mh{};
   int map_bytes = 0;
   bool has_bounds = false;
   float bounds[4] = {0, 0, 0, 0};
@@ -1002,6 +1092,7 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   CUDA_TRY(cudaMalloc(&c->d_map, mh.total_bytes));
   CUDA_TRY(cudaMemcpy(c->d_map, blob.data(), mh.total_bytes, cudaMemcpyHostToDevice));
   c->map_bytes = (int)mh.total_bytes;
+  c->mh = mh;
   return T2D_OK;
 }
 
@@ -1029,7 +1120,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.type_id = c->type_id; A.step_count = c->step_count;
   A.action = action; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
   A.scn_status = scn_status; A.done = done;
-  A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine;
+  A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine; A.mh = c->mh;
   A.map_in_smem = (c->d_map && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
   A.table = c->d_table; A.n_types = c->n_types;
   A.N = c->N; A.M = c->M; A.G = c->G;
@@ -1060,6 +1151,10 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   int wpc = 2;
   for (int w : {8, 4}) {
     if ((tiles + w - 1) / w >= 6LL * c->sm_count) { wpc = w; break; }
+  }
+  if (const char* e = getenv("T2D_WPC")) {   // experiments
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
   }
   const int smem_fixed = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 16;
   const int smem = smem_fixed + wpc * (POSE_PER_WARP * (2 * (int)sizeof(float4) + (int)sizeof(int)) + QCAP * 4 + 2 * POS_EXT_PER_WARP * 4) + 32;
