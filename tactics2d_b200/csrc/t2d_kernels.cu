@@ -214,7 +214,7 @@ __device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* pos
 }
 
 constexpr int QCAP = 192;   // per-warp queue: candidate pairs, then static participants (0..127) + undecided segments (128..191)
-constexpr int POS_EXT_PER_WARP = 448;   // circularly extended x / y arrays: (32 / G) x (1.5 MP + 8) <= 448 floats per warp
+constexpr int POS_EXT_PER_WARP = 704;   // circularly extended x / y arrays: (32 / G) x (1.5 MP + 8) <= 448 floats per warp
 
 // Exact test of one candidate pair (tile indices ti, tj of the same scenario); a hit is recorded for both
 // ends as the minimum partner index (scenario-local), which is what "first hit in list order" means.
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
   while ((1 << mp_shift) < MP) ++mp_shift;
   // circularly extended positions of this scenario: slot k holds participant k mod M, so the partner loop reads
   // consecutive slots (two per 64-bit load) without wrap-around logic
-  const int EXT = (3 * MP) / 2 + 8;
+  const int EXT = (3 * MP) / 2 + 16;   // >= (MP - PPL) + 2 * (partner pairs rounded up to whole words)
   float* posx = s_posx + warp * POS_EXT_PER_WARP + sub * EXT;
   float* posy = s_posy + warp * POS_EXT_PER_WARP + sub * EXT;
   const int Mh = M >> 1;                // partner offsets 1..Mh cover every unordered pair
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
       const bool circle = p.shape == SHAPE_CIRCLE;
       solid_bits |= sol ? (1u << i) : 0u;
       // bounding radius, rounded up so the broadphase is conservative
-      rb[i] = circle ? p.radius : sqrtf(fmaf(p.half_len, p.half_len, p.half_wid * p.half_wid)) * 1.000001f;
+      rb[i] = p.rbound;
       px[i] = sol ? sx[i] : __int_as_float(0x7fc00000);   // NaN: a non-solid slot never passes a distance test
       py[i] = sy[i];
       poseA[t0 + i] = make_float4(px[i], py[i], rb[i], shd[i]);
@@ -627,27 +627,41 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         nx2[i] = make_float2(-px[i], -px[i]);
         ny2[i] = make_float2(-py[i], -py[i]);
       }
-      const int U = Mh > 0 ? (Mh + PPL + 1) >> 1 : 0;   // partner pairs: offsets -(PPL-1) .. >= Mh
+      // partner pairs u = 0 .. U-1 cover offsets -(PPL-1) .. >= Mh; U is rounded up to whole words (the extended
+      // arrays are long enough), so the word body has no bounds test and its loads can be issued back to back
+      constexpr int IPW = 16 / PPL;                        // iterations per 32-bit word (2 * PPL bits each)
+      const int n_words = Mh > 0 ? (((Mh + PPL + 1) >> 1) + IPW - 1) / IPW : 0;
       const float2* bx = reinterpret_cast<const float2*>(posx + m0);
       const float2* by = reinterpret_cast<const float2*>(posy + m0);
-      const int iters_per_word = 16 / PPL;               // 2 * PPL bits per iteration
-      for (int uw = 0; uw * iters_per_word < U; ++uw) {
+      // word 0 also meets the lane's own participants (offset <= 0): drop those verdicts up front
+      unsigned valid0 = 0;
+#pragma unroll
+      for (int uu = 0; uu < IPW; ++uu)
+#pragma unroll
+        for (int i = 0; i < PPL; ++i)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (2 * uu + e - i >= 1) valid0 |= 1u << ((uu * PPL + i) * 2 + e);
+      for (int uw = 0; uw < n_words; ++uw) {
+        float2 X[IPW], Y[IPW];
+#pragma unroll
+        for (int uu = 0; uu < IPW; ++uu) {
+          X[uu] = bx[uw * IPW + uu];
+          Y[uu] = by[uw * IPW + uu];
+        }
         unsigned bits = 0;
 #pragma unroll
-        for (int uu = 0; uu < iters_per_word; ++uu) {
-          const int u = uw * iters_per_word + uu;
-          if (u < U) {
-            const float2 X = bx[u], Y = by[u];
+        for (int uu = 0; uu < IPW; ++uu) {
 #pragma unroll
-            for (int i = 0; i < PPL; ++i) {
-              const float2 dx = __fadd2_rn(X, nx2[i]), dy = __fadd2_rn(Y, ny2[i]);
-              const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-              if (d2.x <= thr[i]) bits |= 1u << ((uu * PPL + i) * 2);
-              if (d2.y <= thr[i]) bits |= 2u << ((uu * PPL + i) * 2);
-            }
+          for (int i = 0; i < PPL; ++i) {
+            const float2 dx = __fadd2_rn(X[uu], nx2[i]), dy = __fadd2_rn(Y[uu], ny2[i]);
+            const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+            if (d2.x <= thr[i]) bits |= 1u << ((uu * PPL + i) * 2);
+            if (d2.y <= thr[i]) bits |= 2u << ((uu * PPL + i) * 2);
           }
         }
-        if (bits) pair_enqueue_bits<PPL>(bits, uw * iters_per_word, t0, tb, m0, M, Mh, queue, qcount);
+        if (uw == 0) bits &= valid0;
+        if (bits) pair_enqueue_bits<PPL>(bits, uw * IPW, t0, tb, m0, M, Mh, queue, qcount);
       }
       __syncwarp();
       T2D_STAMP(4);
@@ -936,12 +950,13 @@ int t2d_set_config(t2d_ctx* c, const t2d_config* cfg) {
 int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   if (!c || !table) return fail(T2D_E_INVALID, "ctx/table is NULL");
   if (n_types <= 0 || n_types > T2D_MAX_TYPES) return fail(T2D_E_INVALID, "n_types must be in 1..64");
-  static_assert(sizeof(t2d_type_params) == sizeof(Params), "type table layout");
+  static_assert(sizeof(t2d_type_params) == sizeof(AbiParams), "type table layout");
+  static_assert(sizeof(Params) == 96, "device type row");
   c->has_pointmass = false;
   float rb_max = 0.0f;
   for (int i = 0; i < n_types; ++i) {
     const t2d_type_params& p = table[i];
-    if (p.shape == T2D_SHAPE_OBB) rb_max = std::max(rb_max, std::sqrt(p.half_len * p.half_len + p.half_wid * p.half_wid) * 1.000002f);
+    if (p.shape == T2D_SHAPE_OBB) rb_max = std::max(rb_max, sqrtf(p.half_len * p.half_len + p.half_wid * p.half_wid) * 1.000002f);
     if (p.shape == T2D_SHAPE_CIRCLE) rb_max = std::max(rb_max, p.radius);
     if (p.model < 0 || p.model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "type table: unknown model id");
     if (p.shape < 0 || p.shape > T2D_SHAPE_NONE) return fail(T2D_E_INVALID, "type table: unknown shape id");
@@ -955,7 +970,15 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   }
   CUDA_TRY(cudaSetDevice(c->device));
   if (!c->d_table) CUDA_TRY(cudaMalloc(&c->d_table, T2D_MAX_TYPES * sizeof(Params)));
-  CUDA_TRY(cudaMemcpy(c->d_table, table, n_types * sizeof(Params), cudaMemcpyHostToDevice));
+  {
+    std::vector<Params> rows(n_types);
+    for (int i = 0; i < n_types; ++i) {
+      AbiParams a;
+      memcpy(&a, &table[i], sizeof(AbiParams));
+      rows[i] = derive_params(a);
+    }
+    CUDA_TRY(cudaMemcpy(c->d_table, rows.data(), n_types * sizeof(Params), cudaMemcpyHostToDevice));
+  }
   c->n_types = n_types;
   c->rb_max = rb_max;
   c->kin_only = true;
@@ -1229,7 +1252,11 @@ int t2d_physics_step(int device, const t2d_type_params* params, int interval_ms,
   if (params->model < 0 || params->model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "unknown model id");
   CUDA_TRY(cudaSetDevice(device));
   PhysArgs A{};
-  memcpy(&A.p, params, sizeof(Params));
+  {
+    AbiParams a;
+    memcpy(&a, params, sizeof(AbiParams));
+    A.p = derive_params(a);
+  }
   A.x = x; A.y = y; A.h = heading; A.v = speed; A.vx = vx; A.vy = vy; A.action = action; A.applied = applied;
   A.n = n;
   const int delta_t = std::min(delta_t_ms, interval_ms);

@@ -53,12 +53,31 @@ constexpr double TWO_PI_D = 6.283185307179586476925286766559;
 constexpr double G_ACC = 9.81;                     // physics_model_base.py:25
 
 // Mirror of t2d_type_params (include/t2d_b200.h); 19 words.
-struct Params {
+struct AbiParams {
   float half_len, half_wid, radius, lf, lr;
   float steer_lo, steer_hi, speed_lo, speed_hi, accel_lo, accel_hi;
   float mass, mass_height, mu, I_z, cf, cr;
   int32_t model, shape;
 };
+
+// The row the kernels read: the ABI row plus constants derived once on the host (24 words = 96 B).
+struct Params : AbiParams {
+  float inv_L;        // 1 / (lf + lr)
+  float lr_over_L;    // lr / (lf + lr)
+  float rbound;       // bounding-circle radius of the collision shape, rounded up
+  float pad0, pad1;
+};
+
+inline Params derive_params(const AbiParams& a) {
+  Params p;
+  static_cast<AbiParams&>(p) = a;
+  const float L = a.lf + a.lr;
+  p.inv_L = 1.0f / L;
+  p.lr_over_L = a.lr / L;
+  p.rbound = a.shape == 1 ? a.radius : sqrtf(a.half_len * a.half_len + a.half_wid * a.half_wid) * 1.000002f;
+  p.pad0 = p.pad1 = 0.0f;
+  return p;
+}
 
 T2D_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // np.clip
 T2D_HD double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -146,14 +165,13 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     float d = clampf(io.steer[i], p[i]->steer_lo, p[i]->steer_hi);  // :193
     io.acc[i] = a[i];
     io.steer[i] = d;
-    float L = p[i]->lf + p[i]->lr;                                  // :85
     float sd, cd;
     sincos_fast(d, &sd, &cd);
     float tan_d = sd / cd;
-    float tb = p[i]->lr / L * tan_d;          // tan(beta), beta = atan(lr/L tan delta)  :127
+    float tb = p[i]->lr_over_L * tan_d;       // tan(beta), beta = atan(lr/L tan delta)  :127  (L = lf + lr, :85)
     float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
     float sb = tb * cb;                          // sin(beta)
-    k[i] = tan_d * cb / L;                       // dphi = v * k                           :141
+    k[i] = tan_d * cb * p[i]->inv_L;             // dphi = v * k                           :141
     kdt[i] = k[i] * dt;
     adt[i] = a[i] * dt;
     float sp, cp;

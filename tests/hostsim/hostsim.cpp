@@ -13,10 +13,10 @@ using namespace t2d;
 extern "C" {
 
 // state arrays in/out; action [n,2] in, applied [n,2] out; ptab: one Params per element
-void hs_physics(int n, const Params* ptab, const int32_t* type_id, int n_steps, double dt, double dt_rem, double interval,
+void hs_physics(int n, const AbiParams* atab, const int32_t* type_id, int n_steps, double dt, double dt_rem, double interval,
                 float* x, float* y, float* h, float* v, float* vx, float* vy, const float* action, float* applied) {
   for (int i = 0; i < n; ++i) {
-    const Params& p = ptab[type_id[i]];
+    const Params p = derive_params(atab[type_id[i]]);
     if (p.model == MODEL_KINEMATICS) {
       KinIO<1> io;
       io.x[0] = x[i]; io.y[0] = y[i]; io.h[0] = h[i]; io.v[0] = v[i];
@@ -39,8 +39,10 @@ void hs_physics(int n, const Params* ptab, const int32_t* type_id, int n_steps, 
 }
 
 // 4-wide kinematics (the kernel's fast path): n must be a multiple of 4
-void hs_kinematics4(int n, const Params* p, int n_steps, double dt, double dt_rem, float* x, float* y, float* h, float* v,
+void hs_kinematics4(int n, const AbiParams* ap, int n_steps, double dt, double dt_rem, float* x, float* y, float* h, float* v,
                     float* vx, float* vy, const float* action) {
+  const Params pd = derive_params(*ap);
+  const Params* p = &pd;
   for (int b = 0; b + 4 <= n; b += 4) {
     KinIO<4> io;
     const Params* pp[4] = {p, p, p, p};
