@@ -251,12 +251,26 @@ def run_ours(args):
         for w, p in zip(worlds, pools):
             w.reset(ones, p)
 
+    # The one exchange of the path: all-gather of this step's done mask.  It runs on a side stream behind an
+    # event, so that the collective of step i overlaps the kernel of step i+1 (the next tick does not consume
+    # it; a learner / reset scheduler does); the streams are joined before the timed region ends.
+    comm_stream = torch.cuda.Stream(device) if world_size > 1 else None
+
     def one_step(i):
         r = i % R
         out = worlds[r].step(actions[r])
         if world_size > 1:
-            dist.all_gather_into_tensor(done_all, out.done)   # the one exchange of the path
+            main = torch.cuda.current_stream(device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            comm_stream.wait_event(ev)
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(done_all, out.done)
         return out
+
+    def join_comm():
+        if world_size > 1:
+            torch.cuda.current_stream(device).wait_stream(comm_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,6 +281,7 @@ def run_ours(args):
     # warm-up (also JIT-free: the library is prebuilt) --------------------------------------------
     for i in range(W):
         one_step(i)
+    join_comm()
     barrier()
 
     # capture the K-step timed region in a CUDA graph ----------------------------------------------
@@ -278,12 +293,14 @@ def run_ours(args):
             with torch.cuda.stream(side):
                 for i in range(min(3, K)):
                     one_step(i)
+                join_comm()
             torch.cuda.current_stream(device).wait_stream(side)
             barrier()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 for i in range(K):
                     one_step(i)
+                join_comm()
             graph = g
         except Exception as e:   # e.g. NCCL capture unsupported: fall back to the eager loop
             if rank == 0:
@@ -302,6 +319,7 @@ def run_ours(args):
         else:
             for i in range(K):
                 one_step(i)
+            join_comm()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -383,7 +401,7 @@ def run_ours(args):
                        "l2_policy": f"inputs larger than L2: {R} world replicas x {bytes_per_launch / 1e6:.1f} MB rotate through the timed steps ({R * bytes_per_launch / 1e6:.0f} MB > {l2_bytes / 1e6:.0f} MB L2)",
                        "timed_region": "CUDA graph of K steps" if graph is not None else "eager launch loop of K steps",
                        "reps": len(reps_ms), "rep_ms_min": min(reps_ms), "rep_ms_max": max(reps_ms),
-                       "collective": "all_gather(done) per step (NCCL)" if world_size > 1 else "none (1 GPU)"},
+                       "collective": "all_gather(done) per step (NCCL, side stream, overlaps the next tick)" if world_size > 1 else "none (1 GPU)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "t2d_step_kernel",
@@ -403,11 +421,21 @@ def run_ours(args):
             except Exception as e:
                 line["cpu_baseline_compiled"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
+    if world_size > 1:
+        # leave without tearing NCCL down under a live CUDA graph that captured its collectives (that teardown
+        # can dead-lock): drop the graph, drain the device, meet the other ranks, then exit hard.
+        graph = None
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     for w in worlds:
         w.close()
-    if world_size > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def main():
