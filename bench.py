@@ -222,6 +222,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world_size > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("T2D_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=device)
         dist.barrier()
     from tactics2d_b200 import BatchedWorld, _lib, synthetic

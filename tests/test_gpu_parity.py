@@ -302,3 +302,55 @@ def test_reset_pool(cuda_device):
         else:
             assert np.array_equal(after["x"][n], before["x"][n]) and cnt[n] == 3
     w.close()
+
+
+# ---------------------------------------------------------------------------- the reference's own map files
+def test_config3_dynamics_on_highD_tile(cuda_device):
+    """BASELINE.json configs[2]: SingleTrackDynamics + map-polyline collision on the highD_1 tile (compiled from
+    /root/reference/data/highD_map/highD_1.osm by tactics2d_b200.map; solid lane markings = road edges)."""
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("highD_1")
+    scene = synthetic.config3(64, 64, seed=13, segments=seg, bounds=bounds)
+    act = lambda t: synthetic.random_actions(1300 + t, scene.shape, accel=(-6, 3), steer=(-0.05, 0.05))
+    stats = _teacher_forced(scene, cuda_device, 5, action_fn=act, any_participant=True)
+    assert stats["static"] > 0
+
+
+def test_config4_mixed_on_inD_tile(cuda_device):
+    """configs[3] (one shard): vehicles / cyclists / pedestrians on the inD_1 intersection (211 collidable segments)."""
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("inD_1")
+    scene = synthetic.with_inactive(synthetic.config4(128, 32, seed=14, segments=seg, bounds=bounds, size=150.0), 0.05, seed=2)
+    act = lambda t: synthetic.random_actions(1400 + t, scene.shape, accel=(-3, 3), steer=(-0.8, 0.8))
+    stats = _teacher_forced(scene, cuda_device, 5, action_fn=act, any_participant=True)
+    assert stats["static"] > 0 and stats["dyn"] > 0
+
+
+def test_config5_m128_on_rounD_tile(cuda_device):
+    """configs[4] (one shard): 128 participants per scenario (a whole warp per scenario) on rounD_0 (411 segments)."""
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("rounD_0")
+    scene = synthetic.config5(24, 128, seed=15, segments=seg, bounds=bounds, size=200.0)
+    stats = _teacher_forced(scene, cuda_device, 4, seed=15, any_participant=True)
+    assert stats["static"] > 0 and stats["dyn"] > 0
+
+
+def test_map_too_large_for_shared_memory_uses_global_path(cuda_device):
+    """A map blob above the shared-memory staging limit is read from global memory (same results)."""
+    from tactics2d_b200 import synthetic
+
+    rng = np.random.default_rng(0)
+    # ~9000 short random segments over a 400 m square: blob > 120 KB
+    p = rng.uniform(0, 400, (9000, 2))
+    d = rng.uniform(-6, 6, (9000, 2))
+    seg = np.concatenate([p, p + d], 1).astype(np.float32)
+    scene = synthetic.config2(12, 64, seed=16, size=400.0)
+    scene.segments = seg
+    stats = _teacher_forced(scene, cuda_device, 2, seed=16, any_participant=True)
+    assert stats["static"] > 0
