@@ -64,6 +64,8 @@ struct StepArgs {
   int map_bytes, map_in_smem;
   int n_types;
   int N, M, G;                     // G = lanes per scenario
+  int g_shift, mp_shift, ext, n_tiles, wpc, table_bytes;   // launch-shape constants (see the kernel prologue)
+  int off_poseA, off_poseB, off_hit, off_queue, off_posx, off_posy, off_qcount, off_bar;   // shared-memory carve
   int n_steps;
   float dt, dt_rem;
   double dt_d, dt_rem_d, interval_d;   // the same steps in double (dynamics / point mass run in fp64)
@@ -189,6 +191,25 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
 
 // Static broadphase, level 1: the clearance field.  One shared-memory load tells whether the pose's
 // bounding circle can reach any segment at all (most participants are nowhere near a wall).
+// near_segments split in two so that the global byte load can be issued early and consumed late:
+// near_fetch returns the quantised clearance under the participant (0 = treat as near: outside the grid but within
+// reach of it; 255 = far), near_decide compares it with the bounding radius.
+__device__ __forceinline__ unsigned near_fetch(const float ax, const float ay, const float rbound, const MapHeader& mh, const uint8_t* fine) {
+  const float r = rbound * 1.0001f + 1e-3f;
+  const float fx = (ax - mh.x0) * mh.inv_cell, fy = (ay - mh.y0) * mh.inv_cell;
+  const int gx = mh.gx, gy = mh.gy;
+  if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)gx && fy < (float)gy)) {
+    const float ox = fmaxf(fmaxf(-fx, fx - (float)gx), 0.0f), oy = fmaxf(fmaxf(-fy, fy - (float)gy), 0.0f);
+    return fmaxf(ox, oy) * mh.cell <= r ? 0u : 255u;   // (NaN position: 255, never near)
+  }
+  const int k = mh.fine;
+  const int ix = min((int)(fx * (float)k), gx * k - 1), iy = min((int)(fy * (float)k), gy * k - 1);
+  return (unsigned)__ldg(fine + (size_t)iy * (gx * k) + ix);
+}
+__device__ __forceinline__ bool near_decide(unsigned q, const float rbound) {
+  return (float)q * CLEAR_QUANT <= rbound * 1.0001f + 1e-3f;
+}
+
 __device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const MapHeader& mh,
                                               const uint8_t* fine) {
   const float r = rbound * 1.0001f + 1e-3f;
@@ -382,20 +403,22 @@ __device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, 
 template <int PPL, bool KIN_ONLY>
 __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // carve: [map blob | 16B aligned] [type table] [pose tiles] [mbarrier]
+  // carve: [map blob | 16B aligned] [type table] [pose tiles, hit mins, queues, positions] [mbarrier]; every
+  // offset, shift and count that depends only on the launch shape comes precomputed from the host
+  // (kernel-parameter constant bank) instead of integer divisions / loops per thread
   const int map_smem_bytes = A.map_in_smem ? A.map_bytes : 0;
+  const int table_bytes = A.table_bytes;
+  const int wpc = A.wpc;
   unsigned char* s_map = smem;
   Params* s_table = reinterpret_cast<Params*>(smem + map_smem_bytes);
-  const int table_bytes = ((A.n_types * (int)sizeof(Params) + 15) / 16) * 16;
-  const int wpc = blockDim.x >> 5;   // warps per CTA (2, 4 or 8: chosen by the host for SM balance)
-  float4* s_poseA = reinterpret_cast<float4*>(smem + map_smem_bytes + table_bytes);
-  float4* s_poseB = s_poseA + wpc * POSE_PER_WARP;
-  int* s_hit = reinterpret_cast<int*>(s_poseB + wpc * POSE_PER_WARP);
-  unsigned* s_queue = reinterpret_cast<unsigned*>(s_hit + wpc * POSE_PER_WARP);
-  float* s_posx = reinterpret_cast<float*>(s_queue + wpc * QCAP);
-  float* s_posy = s_posx + wpc * POS_EXT_PER_WARP;
-  int* s_qcount = reinterpret_cast<int*>(s_posy + wpc * POS_EXT_PER_WARP);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_qcount + ((wpc + 3) & ~3));
+  float4* s_poseA = reinterpret_cast<float4*>(smem + A.off_poseA);
+  float4* s_poseB = reinterpret_cast<float4*>(smem + A.off_poseB);
+  int* s_hit = reinterpret_cast<int*>(smem + A.off_hit);
+  unsigned* s_queue = reinterpret_cast<unsigned*>(smem + A.off_queue);
+  float* s_posx = reinterpret_cast<float*>(smem + A.off_posx);
+  float* s_posy = reinterpret_cast<float*>(smem + A.off_posy);
+  int* s_qcount = reinterpret_cast<int*>(smem + A.off_qcount);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + A.off_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t_entry = A.dbg_clock ? clock64() : 0;
@@ -415,9 +438,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
   bool staged = false;
 
   const int G = A.G, M = A.M;
-  const int spw = 32 / G;               // scenarios per warp
-  const int sub = lane / G;             // scenario slot inside the warp
-  const int gl = lane - sub * G;        // lane inside the group
+  const int spw = 32 >> A.g_shift;      // scenarios per warp
+  const int sub = lane >> A.g_shift;    // scenario slot inside the warp
+  const int gl = lane & (G - 1);        // lane inside the group
   const int m0 = gl * PPL;              // first participant of this lane
   const int MP = G * PPL;               // padded participants per scenario
   // warp-level views of the pose tile; t0 = this lane's first slot in it, tb = its scenario's first slot
@@ -427,24 +450,23 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
   unsigned* queue = s_queue + warp * QCAP;
   int* qcount = s_qcount + warp;
   const int tb = sub * MP, t0 = tb + m0;
-  int mp_shift = 0;
-  while ((1 << mp_shift) < MP) ++mp_shift;
+  const int mp_shift = A.mp_shift;   // MP = 1 << mp_shift
   // circularly extended positions of this scenario: slot k holds participant k mod M, so the partner loop reads
   // consecutive slots (two per 64-bit load) without wrap-around logic
-  const int EXT = (3 * MP) / 2 + 16;   // >= (MP - PPL) + 2 * (partner pairs rounded up to whole words)
+  const int EXT = A.ext;   // (3 MP) / 2 + 16 >= (MP - PPL) + 2 * (partner pairs rounded up to whole words)
   float* posx = s_posx + warp * POS_EXT_PER_WARP + sub * EXT;
   float* posy = s_posy + warp * POS_EXT_PER_WARP + sub * EXT;
   const int Mh = M >> 1;                // partner offsets 1..Mh cover every unordered pair
 
-  const long long n_tiles = ((long long)A.N + spw - 1) / spw;
-  for (long long tile = (long long)blockIdx.x * wpc + warp; tile < n_tiles; tile += (long long)gridDim.x * wpc) {
-    const long long n = tile * spw + sub;
+  const int n_tiles = A.n_tiles;
+  for (int tile = (int)blockIdx.x * wpc + warp; tile < n_tiles; tile += (int)gridDim.x * wpc) {
+    const long long n = (long long)tile * spw + sub;
     const bool scn_ok = n < A.N;
     int nvalid = scn_ok ? min(PPL, M - m0) : 0;
     if (nvalid < 0) nvalid = 0;
     const long long idx0 = n * M + m0;
 
-    #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[tile * 10 + (k)] = clock64(); } while (0)
+    #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[(long long)tile * 10 + (k)] = clock64(); } while (0)
     T2D_STAMP(0);
     // ------------------------------------------------------------------ load
     float sx[PPL], sy[PPL], shd[PPL], sv[PPL], svx[PPL], svy[PPL], a0[PPL], a1[PPL];
@@ -604,6 +626,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     if (lane == 0) *qcount = 0;
     __syncwarp();
 
+    // static broadphase level 1 (clearance field: one byte per participant through L1/L2), issued here so that
+    // its global-load latency hides behind the partner loop
+    unsigned near_q[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i)
+      near_q[i] = (A.map_blob != nullptr && ((solid_bits >> i) & 1u)) ? near_fetch(px[i], py[i], rb[i], A.mh, A.map_fine) : 255u;
+
     T2D_STAMP(3);
     // ------------------------------------------------------------------ dynamic collision
     // Every unordered pair once: participant i tests partners (i+1 .. i+M/2) mod M.  A lane walks the
@@ -695,7 +724,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
       unsigned near_bits = 0;
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
-        if (((solid_bits >> i) & 1u) && near_segments(px[i], py[i], rb[i], A.mh, A.map_fine)) near_bits |= 1u << i;
+        if (((solid_bits >> i) & 1u) && near_decide(near_q[i], rb[i])) near_bits |= 1u << i;
       if (__any_sync(0xffffffffu, near_bits != 0)) {
         if (A.map_in_smem)
           static_phase<PPL>(near_bits, t0, lane, A.mh, reinterpret_cast<const float4*>(s_map + A.mh.off_seg),
@@ -771,8 +800,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     if (A.dbg_clock && lane == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      A.dbg_clock[tile * 10 + 8] = smid;
-      A.dbg_clock[tile * 10 + 9] = t_entry;
+      A.dbg_clock[(long long)tile * 10 + 8] = smid;
+      A.dbg_clock[(long long)tile * 10 + 9] = t_entry;
     }
     __syncwarp();   // pose tile is reused by the next tile
   }
@@ -1179,8 +1208,27 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
   }
-  const int smem_fixed = (A.map_in_smem ? A.map_bytes : 0) + table_bytes + 16;
-  const int smem = smem_fixed + wpc * (POSE_PER_WARP * (2 * (int)sizeof(float4) + (int)sizeof(int)) + QCAP * 4 + 2 * POS_EXT_PER_WARP * 4) + 32;
+  {
+    int off = (A.map_in_smem ? A.map_bytes : 0) + table_bytes;
+    A.off_poseA = off; off += wpc * POSE_PER_WARP * (int)sizeof(float4);
+    A.off_poseB = off; off += wpc * POSE_PER_WARP * (int)sizeof(float4);
+    A.off_hit = off; off += wpc * POSE_PER_WARP * (int)sizeof(int);
+    A.off_queue = off; off += wpc * QCAP * 4;
+    A.off_posx = off; off += wpc * POS_EXT_PER_WARP * 4;
+    A.off_posy = off; off += wpc * POS_EXT_PER_WARP * 4;
+    A.off_qcount = off; off += ((wpc + 3) & ~3) * 4;
+    A.off_bar = off; off += 16;
+    A.wpc = wpc;
+    A.table_bytes = table_bytes;
+    A.n_tiles = (int)tiles;
+    A.g_shift = 0;
+    while ((1 << A.g_shift) < c->G) ++A.g_shift;
+    const int MP = c->G * c->ppl;
+    A.mp_shift = 0;
+    while ((1 << A.mp_shift) < MP) ++A.mp_shift;
+    A.ext = (3 * MP) / 2 + 16;
+  }
+  const int smem = A.off_bar + 16;
   if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");
   using kernel_t = void (*)(StepArgs);
   kernel_t kern;
