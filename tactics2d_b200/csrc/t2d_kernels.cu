@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t_entry = A.dbg_clock ? clock64() : 0;
+  // Programmatic dependent launch: let the next tick's grid start launching now (its prologue - shared-memory
+  // carve, mbarrier, TMA staging of the static table / map - overlaps this grid's tail) ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // Stage the type table and the map tile with TMA bulk copies (UBLKCP) on one mbarrier; the wait sits after
   // the first tile's global loads have been issued, so the staging overlaps the cold HBM reads.
@@ -436,6 +439,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     if (map_smem_bytes > 0) bulk_g2s(s_map, A.map_blob, (uint32_t)map_smem_bytes, s_bar);
   }
   bool staged = false;
+  // ... and wait here, before the first access to the state the previous tick wrote, until that grid has
+  // completed and flushed (no-op when the kernel was not launched as a programmatic dependent).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int G = A.G, M = A.M;
   const int spw = 32 >> A.g_shift;      // scenarios per warp
@@ -906,6 +912,7 @@ struct t2d_ctx {
   int max_smem_optin = 0;
   int configured_smem = -1;
   float rb_max = 0.0f;
+  bool use_pdl = true;             // T2D_PDL=0 disables programmatic dependent launch
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
   int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -947,6 +954,7 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
     if ((v == 2 || v == 4) && 32 * v >= m_participants) ppl = v;   // the packed partner loop needs an even lane base
   }
   c->ppl = ppl;
+  if (const char* e = getenv("T2D_PDL")) c->use_pdl = atoi(e) != 0;
   int g = 1;
   while (g * ppl < m_participants) g <<= 1;
   c->G = g;
@@ -1249,7 +1257,19 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   }
   const long long resident = (long long)c->sm_count * c->occ_val[wpc];
   const int grid = (int)std::max(1LL, std::min(ctas_needed, resident));
-  kern<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(A);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(wpc * 32));
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, A));
+  }
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;
