@@ -24,6 +24,7 @@
  *                        StaticCollision.update           tactics2d/traffic/event_detection/collision.py:37-43
  *                        OutBound.update                  tactics2d/traffic/event_detection/out_bound.py:37-48
  *                        TimeExceed.update                tactics2d/traffic/event_detection/time_exceed.py:26-33
+ *   t2d_set_goal         Arrival.update / NoAction.update  tactics2d/traffic/event_detection/arrival.py:32-47, no_action.py:32-53
  *   t2d_check_events     the same detectors on caller-supplied poses (no physics)
  *   t2d_reset            ScenarioManager.reset / ParticipantBase.reset
  *                                                         tactics2d/envs/parking.py:397-441, participant_base.py:236-246
@@ -145,6 +146,17 @@ int t2d_step(t2d_ctx* ctx, const float* action, uint8_t* flags, int16_t* hit_ind
 
 /* The detectors alone on the bound poses (x, y, heading); no physics, no step counting. */
 int t2d_check_events(t2d_ctx* ctx, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, void* stream);
+
+/* Arrival (tactics2d/traffic/event_detection/arrival.py:32-47) and NoAction (no_action.py:32-53) for the ego
+ * (participant 0) of every scenario, evaluated inside t2d_step.  All pointers are DEVICE arrays owned by the caller:
+ * target [N][5] = (cx, cy, heading, half_len, half_wid) of the target-area rectangle (NULL disables both detectors),
+ * iou_out [N] receives IoU(ego pose, target) (Arrival.update's second return value), last_pose [N][4] and
+ * no_action_count [N] are the detector state (zero them before the first step; t2d_reset clears them).
+ * arrival_threshold: IoU >= threshold -> T2D_STATUS_COMPLETED (reference 0.95); no_action_max_step: more than that
+ * many consecutive ticks with IoU(pose, previous pose) > 0.999 -> T2D_STATUS_NO_ACTION (reference 100; <= 0 disables).
+ * Status priority (envs/parking.py:361-392): time exceeded, no action, out of bound, collision, completed. */
+int t2d_set_goal(t2d_ctx* ctx, const float* target, float arrival_threshold, int no_action_max_step, float* iou_out,
+                 float* last_pose, int32_t* no_action_count);
 
 /* Masked re-initialisation: for every scenario n with mask[n] != 0 copy row pool_index[n] of the
  * [P, M] pool arrays into the bound state and zero step_count[n]. pool_type may be NULL. */

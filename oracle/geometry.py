@@ -105,3 +105,32 @@ def out_of_bound(x, y, ex, ey, bounds):
     out as soon as one corner is *strictly* outside."""
     xmin, xmax, ymin, ymax = bounds
     return (x - ex < xmin) | (x + ex > xmax) | (y - ey < ymin) | (y + ey > ymax)
+
+
+def rect_iou(xa, ya, ha, la, wa, xb, yb, hb, lb, wb):
+    """IoU of two rotated rectangles (scalar float64): ``intersection.area / union.area`` as
+    ``Arrival.update`` (arrival.py:42-46) and ``NoAction.update`` (no_action.py:43-46) compute it with
+    shapely.  Intersection of two convex rings by half-plane clipping, areas by the shoelace formula."""
+    A = obb_corners(xa, ya, ha, la, wa).tolist()
+    B = obb_corners(xb, yb, hb, lb, wb).tolist()
+    poly = A
+    for e in range(4):
+        (x0, y0), (x1, y1) = B[e], B[(e + 1) % 4]
+        ex, ey = x1 - x0, y1 - y0
+        out = []
+        for i in range(len(poly)):
+            p, q = poly[i], poly[(i + 1) % len(poly)]
+            dp = ex * (p[1] - y0) - ey * (p[0] - x0)
+            dq = ex * (q[1] - y0) - ey * (q[0] - x0)
+            if dp >= 0:
+                out.append(p)
+            if (dp >= 0) != (dq >= 0):
+                t = dp / (dp - dq)
+                out.append([p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])])
+        poly = out
+        if not poly:
+            break
+    inter = 0.5 * abs(sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1]
+                          for i in range(len(poly)))) if poly else 0.0
+    union = 4.0 * la * wa + 4.0 * lb * wb - inter
+    return inter / union if union > 0 else 0.0

@@ -6,11 +6,11 @@ The tick the reference performs for ONE ego in ``_ParkingScenarioManager.update`
 1. ``update``  (parking.py:352-356): ``cnt_step += 1``; every participant's physics
    model steps its current state (``oracle.physics``), the new state is appended.
 2. ``check_status`` (parking.py:361-392), on the NEW poses, first hit returns:
-   time-exceed (time_exceed.py:26-33) -> [no-action: a later row] -> out-of-bound
-   (out_bound.py:37-48) -> static collision (collision.py:37-43, first object in
-   list order, ``break``) -> [dynamic collision (collision.py:18-25: the ego against
-   every other participant in list order, ``break``) - unused by the reference envs,
-   appended here after static] -> [arrival: a later row].
+   time-exceed (time_exceed.py:26-33) -> no-action (no_action.py:32-53, ``goal_events``)
+   -> out-of-bound (out_bound.py:37-48) -> static collision (collision.py:37-43, first
+   object in list order, ``break``) -> [dynamic collision (collision.py:18-25: the ego
+   against every other participant in list order, ``break``) - unused by the reference
+   envs, appended here after static] -> arrival (arrival.py:32-47, ``goal_events``).
 3. ``terminated/truncated`` (parking.py:243-248): done = status != NORMAL.
 
 Extensions the reference leaves undefined and this build defines:
@@ -173,3 +173,48 @@ def tick(state, type_id, action, table, step_count, segments=None, bounds=None, 
     cnt = np.asarray(step_count) + 1
     st, done = status(flags, type_id, cnt, max_step, ego_only)
     return new, flags, hi, hs, st, done, cnt
+
+
+def goal_events(x, y, heading, type_id, table, target, last_pose, count, threshold=0.95, no_action_max=100):
+    """Arrival.update (arrival.py:32-47) and NoAction.update (no_action.py:32-53) for the ego (participant 0) of
+    every scenario, on the given (new) poses.  ``last_pose``: [N, 4] (x, y, heading, valid), ``count``: [N].
+    Returns (arrived bool [N], no_action bool [N], iou [N], new_last_pose, new_count)."""
+    N = x.shape[0]
+    p = _gather(table, type_id)
+    arrived = np.zeros(N, bool)
+    noact = np.zeros(N, bool)
+    iou = np.zeros(N, np.float64)
+    new_last = np.array(last_pose, dtype=np.float64)
+    new_count = np.array(count, dtype=np.int64)
+    for n in range(N):
+        if type_id[n, 0] == INACTIVE or p["shape"][n, 0] != OBB:
+            continue
+        ex, ey, eh = float(x[n, 0]), float(y[n, 0]), float(heading[n, 0])
+        el, ew = float(p["half_len"][n, 0]), float(p["half_wid"][n, 0])
+        if no_action_max > 0:
+            if last_pose[n, 3] != 0:
+                i0 = G.rect_iou(ex, ey, eh, el, ew, float(last_pose[n, 0]), float(last_pose[n, 1]), float(last_pose[n, 2]), el, ew)
+                new_count[n] = new_count[n] + 1 if i0 > 0.999 else 0
+            noact[n] = new_count[n] > no_action_max
+        new_last[n] = (ex, ey, eh, 1.0)
+        t = [float(v) for v in target[n]]
+        iou[n] = G.rect_iou(ex, ey, eh, el, ew, *t)
+        arrived[n] = iou[n] >= threshold
+    return arrived, noact, iou, new_last, new_count
+
+
+def status_with_goal(flags, type_id, step_count_new, arrived, noact, max_step=0, ego_only=True):
+    """The full check_status chain (parking.py:361-392); later assignments have higher priority:
+    completed < collision < out of bound < no action < time exceeded."""
+    active = type_id != INACTIVE
+    f = np.where(active, flags, 0)
+    agg = f[:, 0] if ego_only else np.bitwise_or.reduce(f, axis=1)
+    st = np.full(flags.shape[0], NORMAL, np.uint8)
+    st = np.where(arrived, COMPLETED, st)                       # parking.py:387-390
+    st = np.where((agg & (F_DYNAMIC | F_STATIC)) != 0, FAILED, st)   # :381-385
+    st = np.where((agg & F_OUTBOUND) != 0, OUT_BOUND, st)       # :376-379
+    st = np.where(noact, NO_ACTION, st)                         # :371-374
+    if max_step and max_step > 0:
+        st = np.where(step_count_new > max_step, TIME_EXCEEDED, st)   # :366-369
+    st = st.astype(np.uint8)
+    return st, (st != NORMAL).astype(np.uint8)

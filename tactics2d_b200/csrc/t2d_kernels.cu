@@ -73,6 +73,12 @@ struct StepArgs {
   int do_physics, has_bounds, vec_ok, needs_vel_in;
   float bxmin, bxmax, bymin, bymax;
   float rb_max;                    // largest bounding radius in the type table (broadphase threshold)
+  const float* goal_target;        // [N][5] cx, cy, heading, half_len, half_wid of the target area, or nullptr
+  float* goal_iou;                 // [N]
+  float* goal_last_pose;           // [N][4] x, y, heading, valid
+  int32_t* goal_noact_count;       // [N]
+  float goal_threshold;
+  int goal_noact_max;
   long long* dbg_clock;            // optional [n_tiles][8] phase time stamps (T2D_DEBUG_CLOCK); nullptr in production
 };
 
@@ -395,6 +401,28 @@ __device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, 
   int r = out_of_bound_f32(a.x, a.y, a.c, a.s, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax);
   if (r < 0) r = out_of_bound_f64(a.x, a.y, a.h, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax) ? 1 : 0;
   return r != 0;
+}
+
+// Arrival (arrival.py:32-47) and NoAction (no_action.py:32-53) for the ego of scenario n; returns bit0 = arrived,
+// bit1 = no action for more than max_step consecutive ticks.  One lane per scenario, fp64, out of line.
+__device__ __noinline__ unsigned ego_goal_events(const StepArgs& A, long long n, float ex, float ey, float eh, float el, float ew) {
+  unsigned r = 0;
+  float* last = A.goal_last_pose + 4 * n;
+  if (A.goal_noact_max > 0) {
+    int cnt = A.goal_noact_count[n];
+    if (last[3] != 0.0f) {                                          // no_action.py:40-50
+      const double iou = rect_iou_f64(ex, ey, eh, el, ew, last[0], last[1], last[2], el, ew);
+      cnt = iou > 0.999 ? cnt + 1 : 0;
+    }
+    A.goal_noact_count[n] = cnt;
+    if (cnt > A.goal_noact_max) r |= 2u;                            // no_action.py:53
+  }
+  last[0] = ex; last[1] = ey; last[2] = eh; last[3] = 1.0f;         // no_action.py:39,51
+  const float* tg = A.goal_target + 5 * n;
+  const double iou = rect_iou_f64(ex, ey, eh, el, ew, tg[0], tg[1], tg[2], tg[3], tg[4]);   // arrival.py:42-44
+  A.goal_iou[n] = (float)iou;
+  if (iou >= (double)A.goal_threshold) r |= 1u;                     // arrival.py:45
+  return r;
 }
 
 // ---------------------------------------------------------------------------- K1
@@ -794,9 +822,16 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         const int cnt = A.step_count[n] + 1;                         // parking.py:353
         A.step_count[n] = cnt;
         uint8_t st = T2D_STATUS_NORMAL;
+        unsigned goal = 0;
+        if (A.goal_target != nullptr) {   // the ego is participant 0 = this lane's first slot
+          const float4 ea = poseA[t0], eb = poseB[t0];
+          if (ea.x == ea.x && eb.w >= 0.0f) goal = ego_goal_events(A, n, ea.x, ea.y, ea.w, eb.z, eb.w);
+        }
+        if (goal & 1u) st = T2D_STATUS_COMPLETED;                    // parking.py:387-390 (lowest priority)
         if (agg & T2D_F_DYNAMIC) st = T2D_STATUS_FAILED;
         if (agg & T2D_F_STATIC) st = T2D_STATUS_FAILED;              // parking.py:381-385
         if (agg & T2D_F_OUTBOUND) st = T2D_STATUS_OUT_BOUND;         // parking.py:376-379
+        if (goal & 2u) st = T2D_STATUS_NO_ACTION;                    // parking.py:371-374
         if (A.max_step > 0 && cnt > A.max_step) st = T2D_STATUS_TIME_EXCEEDED;  // parking.py:366-369
         if (A.scn_status) A.scn_status[n] = st;
         if (A.done) A.done[n] = st != T2D_STATUS_NORMAL;             // parking.py:243-248
@@ -821,6 +856,8 @@ struct ResetArgs {
   const uint8_t* mask;
   const int32_t* pool_index;
   const float *px, *py, *ph, *pv, *pvx, *pvy;
+  float* goal_last_pose;
+  int32_t* goal_noact_count;
   int N, M, n_pool;
 };
 
@@ -835,7 +872,11 @@ __global__ void t2d_reset_kernel(const __grid_constant__ ResetArgs A) {
     A.x[i] = A.px[s]; A.y[i] = A.py[s]; A.h[i] = A.ph[s]; A.v[i] = A.pv[s];
     A.vx[i] = A.pvx ? A.pvx[s] : A.pv[s] * cosf(A.ph[s]);
     A.vy[i] = A.pvy ? A.pvy[s] : A.pv[s] * sinf(A.ph[s]);
-    if (m == 0) A.step_count[n] = 0;
+    if (m == 0) {
+      A.step_count[n] = 0;
+      if (A.goal_last_pose) A.goal_last_pose[4 * (long long)n + 3] = 0.0f;   // NoAction.reset / last_pose = None
+      if (A.goal_noact_count) A.goal_noact_count[n] = 0;
+    }
   }
 }
 
@@ -912,6 +953,12 @@ struct t2d_ctx {
   int max_smem_optin = 0;
   int configured_smem = -1;
   float rb_max = 0.0f;
+  const float* goal_target = nullptr;
+  float* goal_iou = nullptr;
+  float* goal_last_pose = nullptr;
+  int32_t* goal_noact_count = nullptr;
+  float goal_threshold = 0.95f;
+  int goal_noact_max = 0;
   bool use_pdl = true;             // T2D_PDL=0 disables programmatic dependent launch
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
@@ -1203,6 +1250,8 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
 
   A.rb_max = c->rb_max;
   A.dbg_clock = c->dbg_clock;
+  A.goal_target = c->goal_target; A.goal_iou = c->goal_iou; A.goal_last_pose = c->goal_last_pose;
+  A.goal_noact_count = c->goal_noact_count; A.goal_threshold = c->goal_threshold; A.goal_noact_max = c->goal_noact_max;
   const int table_bytes = ((c->n_types * (int)sizeof(Params) + 15) / 16) * 16;
   const int spw = 32 / c->G;
   const long long tiles = ((long long)c->N + spw - 1) / spw;
@@ -1275,6 +1324,16 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   return T2D_OK;
 }
 
+int t2d_set_goal(t2d_ctx* c, const float* target, float arrival_threshold, int no_action_max_step, float* iou_out, float* last_pose,
+                 int32_t* no_action_count) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (target && (!iou_out || !last_pose || !no_action_count)) return fail(T2D_E_INVALID, "t2d_set_goal: NULL output array");
+  if (target && !(arrival_threshold > 0.0f && arrival_threshold <= 1.0f)) return fail(T2D_E_INVALID, "arrival_threshold must be in (0, 1]");
+  c->goal_target = target; c->goal_iou = iou_out; c->goal_last_pose = last_pose; c->goal_noact_count = no_action_count;
+  c->goal_threshold = arrival_threshold; c->goal_noact_max = no_action_max_step;
+  return T2D_OK;
+}
+
 int t2d_debug_set_clock_buffer(t2d_ctx* c, long long* device_buffer) {
   if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
   c->dbg_clock = device_buffer;
@@ -1301,6 +1360,7 @@ int t2d_reset(t2d_ctx* c, const uint8_t* mask, const int32_t* pool_index, int n_
   A.x = c->x; A.y = c->y; A.h = c->h; A.v = c->v; A.vx = c->vx; A.vy = c->vy; A.step_count = c->step_count;
   A.mask = mask; A.pool_index = pool_index;
   A.px = pool_x; A.py = pool_y; A.ph = pool_heading; A.pv = pool_speed; A.pvx = pool_vx; A.pvy = pool_vy;
+  A.goal_last_pose = c->goal_last_pose; A.goal_noact_count = c->goal_noact_count;
   A.N = c->N; A.M = c->M; A.n_pool = n_pool;
   const long long total = (long long)c->N * c->M;
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);

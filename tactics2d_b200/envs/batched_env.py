@@ -8,8 +8,8 @@ Keeps the contract of the reference's single-ego envs (``tactics2d/envs/parking.
 * the action order is ``[steering, accel]`` (parking.py:239); out-of-range actions are clipped by the physics
   model, not rejected (single_track_kinematics.py:192-193);
 * ``terminated`` iff the scenario status is COMPLETED; ``truncated`` iff the scenario or the ego's traffic
-  status is not NORMAL (parking.py:243-248) - with the detectors of this hot path (time limit, out-of-bound,
-  static and dynamic collision) a scenario never completes, so every ``done`` is a truncation;
+  status is not NORMAL (parking.py:243-248); without a ``target`` a scenario never completes, so every ``done``
+  is a truncation;
 * the status priority time-exceed -> out-of-bound -> collision (parking.py:361-392);
 * reward shape of ``ParkingEnv._get_reward`` (parking.py:148-190) for the events that exist here:
   -5 collision / out-of-bound, -1 time exceeded, else a small time penalty ``-tanh(t / max_step) * 0.001``.
@@ -41,8 +41,12 @@ class BatchedTrafficEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, scene, device="cuda:0", max_step: int = 1000, step_size: int = 100, delta_t: int = 5,
-                 any_participant: bool = False, auto_reset: bool = True):
-        """``scene``: a :class:`tactics2d_b200.synthetic.Scene` (initial states, types, map tile, bounds)."""
+                 any_participant: bool = False, auto_reset: bool = True, target=None, arrival_threshold: float = 0.95,
+                 no_action_max_step: int = 100):
+        """``scene``: a :class:`tactics2d_b200.synthetic.Scene` (initial states, types, map tile, bounds);
+        ``target``: optional [N, 5] target areas (cx, cy, heading, half_len, half_wid) for the egos - enables the
+        ``Arrival`` (-> COMPLETED / ``terminated``) and ``NoAction`` detectors and the IoU reward terms of
+        ``ParkingEnv._get_reward`` (parking.py:148-190)."""
         import torch
 
         self.scene = scene
@@ -60,6 +64,10 @@ class BatchedTrafficEnv:
         self.scenario_manager.set_initial_state(self._pool)
         self._action = torch.zeros((n, m, 2), dtype=torch.float32, device=dev)
         self._rng = np.random.default_rng(0)
+        self._max_iou = None
+        if target is not None:
+            self.world.set_goal(target, arrival_threshold, no_action_max_step)
+            self._max_iou = torch.full((n,), -float("inf"), dtype=torch.float32, device=dev)
         self.observation_space = {"shape": (n, m, 6), "dtype": "float32"}
         self.action_space = {"shape": (n, 2), "low": (-np.inf, -np.inf), "high": (np.inf, np.inf)}
 
@@ -82,6 +90,8 @@ class BatchedTrafficEnv:
             perm = torch.from_numpy(self._rng.permutation(self.num_envs).astype(np.int32)).to(self.world.device)
         self.world.type_id.copy_(self._type_id)
         self.scenario_manager.reset(pool_index=perm)
+        if self._max_iou is not None:
+            self._max_iou.fill_(-float("inf"))
         status = torch.full((self.num_envs,), int(ScenarioStatus.NORMAL), dtype=torch.uint8, device=self.world.device)
         traffic = torch.full((self.num_envs, self.num_participants), int(TrafficStatus.NORMAL), dtype=torch.uint8,
                              device=self.world.device)
@@ -112,9 +122,13 @@ class BatchedTrafficEnv:
         truncated = (~terminated) & ((status != int(ScenarioStatus.NORMAL)) | (traffic[:, 0] != int(TrafficStatus.NORMAL)))
         reward = self._get_reward(status, traffic[:, 0])
         info = self._info(status.clone(), traffic, r.flags.clone(), r.hit_index.clone(), r.hit_segment.clone())
+        if r.iou is not None:
+            info["iou"] = r.iou.clone()
         if self.auto_reset:
             done = (terminated | truncated).to(torch.uint8)
             self.scenario_manager.reset(mask=done)
+            if self._max_iou is not None:
+                self._max_iou = torch.where(done.bool(), torch.full_like(self._max_iou, -float("inf")), self._max_iou)
         return self._obs(), reward, terminated, truncated, info
 
     def _get_reward(self, scenario_status, ego_traffic_status):
@@ -123,6 +137,13 @@ class BatchedTrafficEnv:
 
         t = self.world.step_count.to(torch.float32)
         reward = -torch.tanh(t / float(self.max_step)) * 0.001
+        iou = self.world._out.iou
+        if iou is not None:   # parking.py:166-172: first the IoU itself, then its improvement over the best so far
+            first = torch.isinf(self._max_iou)
+            reward = reward + torch.where(first, iou, iou - self._max_iou)
+            self._max_iou = torch.maximum(self._max_iou, iou)
+            reward = torch.where(scenario_status == int(ScenarioStatus.COMPLETED), torch.full_like(reward, 5.0), reward)
+            reward = torch.where(scenario_status == int(ScenarioStatus.NO_ACTION), torch.full_like(reward, -1.0), reward)
         reward = torch.where(scenario_status == int(ScenarioStatus.TIME_EXCEEDED), torch.full_like(reward, -1.0), reward)
         reward = torch.where(scenario_status == int(ScenarioStatus.OUT_BOUND), torch.full_like(reward, -5.0), reward)
         collided = (ego_traffic_status == int(TrafficStatus.COLLISION_STATIC)) | (ego_traffic_status == int(TrafficStatus.COLLISION_DYNAMIC))

@@ -1,8 +1,8 @@
-"""Detectors on this hot path (reference ``tactics2d/traffic/event_detection/__init__.py:7-26``).  ``NoAction``
-and ``Arrival`` (IoU based) are "next" rows of SURVEY.md section 8(f); ``OffRoute`` / ``OffLane`` are
-unused / a stub in the reference."""
+"""Detectors on this hot path (reference ``tactics2d/traffic/event_detection/__init__.py:7-26``), including the
+IoU based ``Arrival`` / ``NoAction``.  ``OffRoute`` / ``OffLane`` are unused / a
+stub in the reference."""
 
-from .detectors import DynamicCollision, OutBound, StaticCollision, TimeExceed
+from .detectors import Arrival, DynamicCollision, NoAction, OutBound, StaticCollision, TimeExceed
 from .event_base import EventBase
 
-__all__ = ["EventBase", "DynamicCollision", "StaticCollision", "OutBound", "TimeExceed"]
+__all__ = ["EventBase", "DynamicCollision", "StaticCollision", "OutBound", "TimeExceed", "Arrival", "NoAction"]

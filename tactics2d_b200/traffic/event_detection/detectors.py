@@ -88,3 +88,45 @@ class TimeExceed(EventBase):
         self.cnt_step = 0
         if world is not None:
             world.step_count.zero_()
+
+
+class Arrival(EventBase):
+    """``Arrival`` (reference arrival.py:12-50): IoU of the ego's pose with the target area, completed when
+    ``iou >= threshold`` (default 0.95).  Batched: ``reset(target, world)`` installs one target rectangle per
+    scenario, ``update(world)`` returns ``(is_completed bool [N], iou fp32 [N])`` of the last ``step``."""
+
+    def __init__(self, target_area=None, threshold: float = 0.95):
+        self.target_area = target_area   # [N, 5] = (cx, cy, heading, half_len, half_wid)
+        self.threshold = threshold
+
+    def update(self, world):
+        r = world._out
+        if r.iou is None:
+            raise RuntimeError("no target area: call Arrival.reset(target_area, world) / world.set_goal first")
+        return r.iou >= self.threshold, r.iou
+
+    def reset(self, target_area=None, world=None, no_action_max_step: int = 100):
+        self.target_area = target_area
+        if world is not None:
+            world.set_goal(target_area, self.threshold, no_action_max_step)
+
+
+class NoAction(EventBase):
+    """``NoAction`` (reference no_action.py:12-58): counts consecutive ticks in which the ego's pose overlaps its
+    previous pose with IoU > 0.999; fires when the count exceeds ``max_step``.  The counter lives on the device
+    (``world.set_goal(..., no_action_max_step=max_step)``); ``update(world)`` reads it."""
+
+    def __init__(self, max_step=100):
+        self.max_step = max_step
+        self.cnt_no_action = 0
+
+    def update(self, world):
+        if world._goal is None:
+            raise RuntimeError("NoAction needs world.set_goal(target, no_action_max_step=...)")
+        return world._goal["count"] > self.max_step
+
+    def reset(self, world=None):
+        self.cnt_no_action = 0
+        if world is not None and world._goal is not None:
+            world._goal["count"].zero_()
+            world._goal["last_pose"].zero_()

@@ -36,6 +36,7 @@ class StepResult:
     hit_segment: torch.Tensor  # int16 [N, M]: lowest colliding map segment index or -1
     status: torch.Tensor       # uint8 [N]: ScenarioStatus
     done: torch.Tensor         # uint8 [N]
+    iou: Optional[torch.Tensor] = None   # fp32 [N]: IoU(ego pose, target area) when a goal is set (Arrival.update)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -85,6 +86,7 @@ class BatchedWorld:
         self._bind()
         self.segments = None
         self.bounds = None
+        self._goal = None
 
     # ------------------------------------------------------------------ plumbing
     def _bind(self):
@@ -131,6 +133,26 @@ class BatchedWorld:
             C.c_void_p(0 if b is None else b.ctypes.data), float(cell_size)))
         self.segments = seg
         self.bounds = None if b is None else tuple(float(v) for v in b)
+
+    def set_goal(self, target=None, arrival_threshold: float = 0.95, no_action_max_step: int = 100):
+        """Target area per scenario for the ego (participant 0): array [N, 5] = (cx, cy, heading, half_len, half_wid),
+        or None to disable.  Enables ``Arrival`` (IoU >= threshold -> COMPLETED, arrival.py:32-47) and ``NoAction``
+        (IoU with the previous pose > 0.999 for more than ``no_action_max_step`` ticks, no_action.py:32-53) inside
+        ``step``; ``StepResult.iou`` then holds the ego/target IoU."""
+        if target is None:
+            self._goal = None
+            self._out.iou = None
+            _lib.check(self.lib.t2d_set_goal(self._ctx, _ptr(None), 0.95, 0, _ptr(None), _ptr(None), _ptr(None)))
+            return
+        t = torch.as_tensor(np.asarray(target, dtype=np.float32) if not torch.is_tensor(target) else target)
+        t = t.to(device=self.device, dtype=torch.float32).reshape(self.N, 5).contiguous()
+        self._goal = dict(target=t, iou=torch.zeros(self.N, dtype=torch.float32, device=self.device),
+                          last_pose=torch.zeros((self.N, 4), dtype=torch.float32, device=self.device),
+                          count=torch.zeros(self.N, dtype=torch.int32, device=self.device))
+        self._out.iou = self._goal["iou"]
+        g = self._goal
+        _lib.check(self.lib.t2d_set_goal(self._ctx, _ptr(g["target"]), float(arrival_threshold), int(no_action_max_step),
+                                         _ptr(g["iou"]), _ptr(g["last_pose"]), _ptr(g["count"])))
 
     # ------------------------------------------------------------------ state
     def set_state(self, x, y, heading, speed=None, vx=None, vy=None, type_id=None):

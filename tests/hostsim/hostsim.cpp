@@ -100,4 +100,12 @@ void hs_outbound(int n, const float* a, const float* bounds, int32_t* out_f32, i
 }
 
 float hs_wrap(float phi) { return wrap_two_pi(phi); }
+
+// rows: x, y, heading, l, w (fp32, as the kernel sees them)
+void hs_rect_iou(int n, const float* a, const float* b, double* out) {
+  for (int i = 0; i < n; ++i) {
+    const float* p = a + 5 * i; const float* q = b + 5 * i;
+    out[i] = rect_iou_f64(p[0], p[1], p[2], p[3], p[4], q[0], q[1], q[2], q[3], q[4]);
+  }
+}
 }

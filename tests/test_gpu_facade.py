@@ -223,3 +223,89 @@ def test_batched_env_contract(cuda_device):
     assert total_done >= 64   # the 5-step limit ends every scenario at least once
     # ego speed grew under the (steer, accel) action order: accel = 1 m/s^2 was applied to `speed`
     env.close()
+
+
+def test_arrival_and_no_action_detectors(cuda_device):
+    """Arrival (IoU >= 0.95 -> COMPLETED) and NoAction (pose IoU > 0.999 for more than max_step ticks -> NO_ACTION)
+    for the ego of every scenario, against the float64 oracle; status priority of envs/parking.py:361-392."""
+    import torch
+
+    from oracle import scenario as O
+    from tactics2d_b200 import BatchedWorld, TypeTable, synthetic
+    from tactics2d_b200.traffic import ScenarioStatus
+    from tactics2d_b200.traffic.event_detection import Arrival, NoAction
+
+    n, m = 48, 8
+    scene = synthetic.config2(n, m, seed=31, size=120.0)
+    table = scene.table.as_oracle_table()
+    rng = np.random.default_rng(7)
+    # targets: scenario k's target sits ahead of the ego so that several egos arrive within a few ticks
+    hl = table["half_len"][scene.type_id[:, 0]].astype(np.float32)
+    hw = table["half_wid"][scene.type_id[:, 0]].astype(np.float32)
+    dist = rng.uniform(0.0, 1.5, n).astype(np.float32)
+    tx = scene.x[:, 0] + dist * np.cos(scene.heading[:, 0])
+    ty = scene.y[:, 0] + dist * np.sin(scene.heading[:, 0])
+    target = np.stack([tx, ty, scene.heading[:, 0], hl, hw], 1).astype(np.float32)
+    speed = scene.speed.copy()
+    speed[:, 0] = rng.uniform(0.0, 4.0, n)
+    speed[: n // 3, 0] = 0.0     # a third of the egos stand still -> NoAction
+    w = BatchedWorld(n, m, scene.table, device=cuda_device, max_step=40)
+    w.set_map(None, (-500.0, 500.0, -500.0, 500.0))
+    w.set_state(scene.x, scene.y, scene.heading, speed, type_id=scene.type_id)
+    arrival, noaction = Arrival(threshold=0.95), NoAction(max_step=3)
+    arrival.reset(target, w, no_action_max_step=3)
+    act = torch.zeros((n, m, 2), device=cuda_device)
+    last = np.zeros((n, 4))
+    count = np.zeros(n, np.int64)
+    seen = set()
+    for t in range(8):
+        r = w.step(act)
+        torch.cuda.synchronize()
+        got = w.state_numpy()
+        arrived, noact, iou, last, count = O.goal_events(got["x"], got["y"], got["heading"], scene.type_id, table, target.astype(np.float64),
+                                                        last, count, 0.95, 3)
+        fl, _, _ = O.events(got["x"], got["y"], got["heading"], scene.type_id, table, None, (-500.0, 500.0, -500.0, 500.0))
+        st, done = O.status_with_goal(fl, scene.type_id, np.full(n, t + 1), arrived, noact, 40, ego_only=True)
+        np.testing.assert_allclose(r.iou.cpu().numpy(), iou, atol=2e-6)
+        # thresholds: exact except within 1e-6 of the IoU threshold
+        clear = np.abs(iou - 0.95) > 1e-6
+        assert np.array_equal(r.status.cpu().numpy()[clear], st[clear])
+        assert np.array_equal(w._goal["count"].cpu().numpy(), count)
+        done_a, iou_a = arrival.update(w)
+        assert np.array_equal(done_a.cpu().numpy()[clear], arrived[clear])
+        assert np.array_equal(noaction.update(w).cpu().numpy(), noact)
+        seen |= set(np.unique(st).tolist())
+    assert {int(ScenarioStatus.COMPLETED), int(ScenarioStatus.NO_ACTION), int(ScenarioStatus.NORMAL)} <= seen
+    # reset clears the detector state of the masked scenarios
+    mask = torch.zeros(n, dtype=torch.uint8, device=cuda_device)
+    mask[:5] = 1
+    pool = {k: torch.from_numpy(v).to(cuda_device) for k, v in scene.state().items()}
+    w.reset(mask, pool)
+    torch.cuda.synchronize()
+    assert (w._goal["count"][:5] == 0).all() and (w._goal["last_pose"][:5, 3] == 0).all() and (w._goal["last_pose"][5:, 3] == 1).all()
+    w.close()
+
+
+def test_batched_env_with_targets_terminates_on_arrival(cuda_device):
+    import torch
+
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.envs import BatchedTrafficEnv
+    from tactics2d_b200.traffic import ScenarioStatus
+
+    scene = synthetic.config2(32, 4, seed=5, size=300.0)
+    t = scene.table.as_oracle_table()
+    tid = scene.type_id[:, 0]
+    target = np.stack([scene.x[:, 0] + 0.3 * np.cos(scene.heading[:, 0]), scene.y[:, 0] + 0.3 * np.sin(scene.heading[:, 0]),
+                       scene.heading[:, 0], t["half_len"][tid], t["half_wid"][tid]], 1).astype(np.float32)
+    env = BatchedTrafficEnv(scene, device=cuda_device, max_step=50, auto_reset=False, target=target, no_action_max_step=1000)
+    obs, info = env.reset(seed=1)
+    env.world.speed[:, 0] = 3.0   # 0.3 m per tick straight at the target
+    action = torch.zeros((32, 2), device=cuda_device)
+    obs, reward, terminated, truncated, info = env.step(action)
+    st = info["scenario_status"]
+    ok = (st == int(ScenarioStatus.COMPLETED)) | (st == int(ScenarioStatus.FAILED)) | (st == int(ScenarioStatus.OUT_BOUND))
+    assert ok.all() and terminated.sum() >= 20
+    assert (terminated == (st == int(ScenarioStatus.COMPLETED))).all() and not (terminated & truncated).any()
+    assert (reward[terminated] == 5.0).all() and (info["iou"][terminated] >= 0.95).all()
+    env.close()

@@ -230,3 +230,29 @@ def test_filtered_segment_and_outbound_predicates(hostsim):
     assert np.array_equal(ex.astype(bool), ref)
     d = f32 >= 0
     assert np.array_equal(f32[d].astype(bool), ref[d]) and 0.1 < ref.mean() < 0.9
+
+
+def test_rect_iou_matches_oracle_and_monte_carlo(hostsim):
+    rng = np.random.default_rng(11)
+    n = 1500
+    a = np.zeros((n, 5), np.float32)
+    b = np.zeros((n, 5), np.float32)
+    a[:, :2] = rng.uniform(-5, 5, (n, 2)); a[:, 2] = rng.uniform(0, 6.28, n); a[:, 3] = rng.uniform(.5, 3, n); a[:, 4] = rng.uniform(.3, 1.5, n)
+    b[:, :2] = a[:, :2] + rng.uniform(-2, 2, (n, 2)); b[:, 2] = rng.uniform(0, 6.28, n); b[:, 3] = rng.uniform(.5, 3, n); b[:, 4] = rng.uniform(.3, 1.5, n)
+    b[:40] = a[:40]
+    out = np.zeros(n)
+    hostsim.hs_rect_iou(C.c_int(n), _p(a), _p(b), _p(out))
+    ref = np.array([G.rect_iou(*map(float, a[i]), *map(float, b[i])) for i in range(n)])
+    assert np.abs(out - ref).max() < 1e-13 and np.allclose(out[:40], 1.0) and 0.1 < ref.mean() < 0.6
+    # independent check: Monte-Carlo area ratio on a few pairs
+    pts = rng.uniform(-12, 12, (600000, 2))
+
+    def inside(r):
+        c, s = np.cos(r[2]), np.sin(r[2])
+        dx, dy = pts[:, 0] - r[0], pts[:, 1] - r[1]
+        return (np.abs(dx * c + dy * s) <= r[3]) & (np.abs(dy * c - dx * s) <= r[4])
+
+    for i in (100, 200, 300):
+        ia, ib = inside(a[i].astype(float)), inside(b[i].astype(float))
+        mc = (ia & ib).sum() / max((ia | ib).sum(), 1)
+        assert abs(mc - ref[i]) < 0.02
