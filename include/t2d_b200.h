@@ -25,6 +25,7 @@
  *                        OutBound.update                  tactics2d/traffic/event_detection/out_bound.py:37-48
  *                        TimeExceed.update                tactics2d/traffic/event_detection/time_exceed.py:26-33
  *   t2d_set_goal         Arrival.update / NoAction.update  tactics2d/traffic/event_detection/arrival.py:32-47, no_action.py:32-53
+ *   t2d_lidar_scan       SingleLineLidar._scan_obstacles   tactics2d/sensor/lidar.py:128-221
  *   t2d_check_events     the same detectors on caller-supplied poses (no physics)
  *   t2d_reset            ScenarioManager.reset / ParticipantBase.reset
  *                                                         tactics2d/envs/parking.py:397-441, participant_base.py:236-246
@@ -163,6 +164,13 @@ int t2d_set_goal(t2d_ctx* ctx, const float* target, float arrival_threshold, int
 int t2d_reset(t2d_ctx* ctx, const uint8_t* mask, const int32_t* pool_index, int n_pool, const float* pool_x,
               const float* pool_y, const float* pool_heading, const float* pool_speed, const float* pool_vx,
               const float* pool_vy, void* stream);
+
+/* Single-line lidar of the ego (participant 0) of every scenario: SingleLineLidar._scan_obstacles
+ * (tactics2d/sensor/lidar.py:128-221).  n_beams = point_density (lidar.py:49), max_range = perception range;
+ * beam_cos_sin: DEVICE double [n_beams][2] = (cos, sin) of the beam angles linspace(0, 2 pi, n_beams, endpoint=False)
+ * (lidar.py:160); scan: DEVICE float [N][n_beams], +inf where nothing is hit within the range.  Obstacles are the map
+ * segments given to t2d_set_map and the pose rings of the other box-shaped participants. */
+int t2d_lidar_scan(t2d_ctx* ctx, int n_beams, float max_range, const double* beam_cos_sin, float* scan, void* stream);
 
 /* Flat batch of `n` independent participants through ONE model (PhysicsModelBase.step):
  * state arrays are read and written in place; action [n, 2]; applied [n, 2] (may be NULL)

@@ -45,6 +45,7 @@ SYMBOLS = {
     "t2d_check_events": (C.c_int, [_P] + [_P] * 4),
     "t2d_set_goal": (C.c_int, [_P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "t2d_reset": (C.c_int, [_P, _P, _P, C.c_int] + [_P] * 7),
+    "t2d_lidar_scan": (C.c_int, [_P, C.c_int, C.c_float, _P, _P, _P]),
     "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 9),
     "t2d_debug_set_clock_buffer": (C.c_int, [_P, _P]),
     "t2d_launch_count": (C.c_int64, []),

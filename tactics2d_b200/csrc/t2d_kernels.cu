@@ -913,6 +913,137 @@ __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------- K4
+// Single-line lidar of the ego (participant 0) of every scenario: SingleLineLidar._scan_obstacles
+// (tactics2d/sensor/lidar.py:128-221).  Obstacle edges = the map's collidable segments (the reference takes the
+// exteriors of `area.type_ == "obstacle"`, :137-143) + the pose rings of the other box-shaped participants (:146-153;
+// a Pedestrian's pose is not a ring and is skipped there too), transformed into the ego frame (:105-126); per beam
+// the reference's determinant intersection with its 1e-8 slack box filters (:160-213), min over edges, clip to the
+// range, range -> inf.  One warp per scenario: the warp stages the edges that can matter (distance to the ego
+// < range) in shared memory in chunks, then every lane scans its beams (b = lane, lane + 32, ...) over the chunk.
+// fp64 throughout (from the fp32 state): the scan equals the float64 oracle to rounding, and B200 issues DFMA at
+// half the FFMA rate.
+constexpr int LIDAR_EDGES = 320;   // edges per shared-memory chunk per warp (4 doubles each)
+constexpr int LIDAR_WARPS = 4;
+
+struct LidarArgs {
+  const float *x, *y, *h;
+  const uint8_t* type_id;
+  const Params* table;
+  int n_types;
+  const unsigned char* map_blob;
+  MapHeader mh;
+  const double* beam_cs;   // [n_beams][2] cos, sin of the beam angles (host float64)
+  float* scan;             // [N][n_beams]
+  int N, M, n_beams;
+  double range;
+};
+
+__device__ __forceinline__ double point_segment_dist2(double x1, double y1, double x2, double y2) {   // from the origin
+  const double dx = x2 - x1, dy = y2 - y1, dd = dx * dx + dy * dy;
+  double t = dd > 0.0 ? -(x1 * dx + y1 * dy) / dd : 0.0;
+  t = fmin(fmax(t, 0.0), 1.0);
+  const double ex = x1 + t * dx, ey = y1 + t * dy;
+  return ex * ex + ey * ey;
+}
+
+__global__ void __launch_bounds__(LIDAR_WARPS * 32) t2d_lidar_kernel(const __grid_constant__ LidarArgs A) {
+  __shared__ double s_edge[LIDAR_WARPS][LIDAR_EDGES][4];
+  __shared__ int s_cnt[LIDAR_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n = (long long)blockIdx.x * LIDAR_WARPS + warp;
+  if (n >= A.N) return;
+  double(*edge)[4] = s_edge[warp];
+  int* cnt = &s_cnt[warp];
+  const long long base = n * A.M;
+  const int t_ego = A.type_id[base];
+  float* out = A.scan + n * A.n_beams;
+  if (t_ego >= A.n_types) {   // no ego: nothing is seen
+    for (int b = lane; b < A.n_beams; b += 32) out[b] = INFINITY;
+    return;
+  }
+  const double x0 = A.x[base], y0 = A.y[base], th = A.h[base];
+  double sa, ca;
+  sincos(th, &sa, &ca);
+  const double xoff = -x0 * ca - y0 * sa, yoff = x0 * sa - y0 * ca;   // lidar.py:116-121
+  const double R = A.range, R2 = R * R;
+  // beams of this lane: running minimum of the squared distance
+  constexpr int MAXB = 16;   // beams per lane handled in registers per pass (n_beams <= 512 per pass)
+  const int n_edges_part = (A.M - 1) * 4;
+  const float4* seg = A.map_blob ? reinterpret_cast<const float4*>(A.map_blob + A.mh.off_seg) : nullptr;
+  const int n_seg = A.map_blob ? A.mh.n_seg : 0;
+  const int total_src = n_edges_part + n_seg;
+  for (int b0 = 0; b0 < A.n_beams; b0 += 32 * MAXB) {
+    double best[MAXB];
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k) best[k] = INFINITY;
+    for (int src0 = 0; src0 < total_src; src0 += LIDAR_EDGES) {
+      // ---- stage one chunk of candidate edges (ego frame), compacted
+      if (lane == 0) *cnt = 0;
+      __syncwarp();
+      const int src1 = min(src0 + LIDAR_EDGES, total_src);
+      for (int e = src0 + lane; e < src1; e += 32) {
+        double gx1, gy1, gx2, gy2;
+        bool ok = true;
+        if (e < n_edges_part) {
+          const int j = 1 + e / 4, k = e & 3;
+          const int tj = A.type_id[base + j];
+          ok = tj < A.n_types && A.table[tj].shape == SHAPE_OBB;
+          if (ok) {
+            double cx[4], cy[4];
+            rect_corners_f64(A.x[base + j], A.y[base + j], A.h[base + j], A.table[tj].half_len, A.table[tj].half_wid, cx, cy);
+            gx1 = cx[k]; gy1 = cy[k]; gx2 = cx[(k + 1) & 3]; gy2 = cy[(k + 1) & 3];
+          }
+        } else {
+          const float4 sg = seg[e - n_edges_part];
+          gx1 = sg.x; gy1 = sg.y; gx2 = sg.z; gy2 = sg.w;
+        }
+        if (ok) {
+          const double x1 = ca * gx1 + sa * gy1 + xoff, y1 = -sa * gx1 + ca * gy1 + yoff;   // affine [a, b, -b, a, xoff, yoff]
+          const double x2 = ca * gx2 + sa * gy2 + xoff, y2 = -sa * gx2 + ca * gy2 + yoff;
+          if (point_segment_dist2(x1, y1, x2, y2) < R2 * 1.0000001 + 1e-9) {
+            const int slot = atomicAdd(cnt, 1);
+            edge[slot][0] = x1; edge[slot][1] = y1; edge[slot][2] = x2; edge[slot][3] = y2;
+          }
+        }
+      }
+      __syncwarp();
+      const int n_e = *cnt;
+      // ---- scan the beams of this lane over the chunk (lidar.py:160-213)
+      for (int i = 0; i < n_e; ++i) {
+        const double x1 = edge[i][0], y1 = edge[i][1], x2 = edge[i][2], y2 = edge[i][3];
+        const double d = y2 - y1, e = x1 - x2, f = y1 * x2 - x1 * y2;
+        const double xlo = fmin(x1, x2) - 1e-8, xhi = fmax(x1, x2) + 1e-8, ylo = fmin(y1, y2) - 1e-8, yhi = fmax(y1, y2) + 1e-8;
+#pragma unroll
+        for (int k = 0; k < MAXB; ++k) {
+          const int b = b0 + lane + 32 * k;
+          if (b < A.n_beams) {
+            const double cb = A.beam_cs[2 * b], sb = A.beam_cs[2 * b + 1];
+            const double a_ = sb, b_ = -cb;
+            const double det = a_ * e - b_ * d;
+            if (det != 0.0) {
+              const double rx = (b_ * f) / det, ry = (-a_ * f) / det;
+              const double lx = cb * R, ly = sb * R;
+              const bool okx = !(rx > fmax(1e-8, lx) + 1e-8) && !(rx < fmin(-1e-8, lx) - 1e-8) && !(rx > xhi) && !(rx < xlo);
+              const bool oky = !(ry > fmax(1e-8, ly) + 1e-8) && !(ry < fmin(-1e-8, ly) - 1e-8) && !(ry > yhi) && !(ry < ylo);
+              if (okx && oky) best[k] = fmin(best[k], rx * rx + ry * ry);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k) {
+      const int b = b0 + lane + 32 * k;
+      if (b < A.n_beams) {
+        const double dist = sqrt(best[k]);
+        out[b] = dist < R ? (float)dist : INFINITY;   // clip to the range, range -> inf (:211-213)
+      }
+    }
+  }
+}
+
 }  // namespace t2d
 
 // =============================================================================================
@@ -1365,6 +1496,23 @@ int t2d_reset(t2d_ctx* c, const uint8_t* mask, const int32_t* pool_index, int n_
   const long long total = (long long)c->N * c->M;
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
   t2d_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+int t2d_lidar_scan(t2d_ctx* c, int n_beams, float max_range, const double* beam_cos_sin, float* scan, void* stream) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
+  if (!c->d_table || c->n_types == 0) return fail(T2D_E_STATE, "type table not set: call t2d_set_type_table first");
+  if (n_beams <= 0 || !(max_range > 0.0f) || !beam_cos_sin || !scan) return fail(T2D_E_INVALID, "t2d_lidar_scan: bad argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  LidarArgs A{};
+  A.x = c->x; A.y = c->y; A.h = c->h; A.type_id = c->type_id; A.table = c->d_table; A.n_types = c->n_types;
+  A.map_blob = c->d_map; A.mh = c->mh; A.beam_cs = beam_cos_sin; A.scan = scan;
+  A.N = c->N; A.M = c->M; A.n_beams = n_beams; A.range = (double)max_range;
+  const int grid = (c->N + LIDAR_WARPS - 1) / LIDAR_WARPS;
+  t2d_lidar_kernel<<<grid, LIDAR_WARPS * 32, 0, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;

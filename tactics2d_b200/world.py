@@ -199,6 +199,20 @@ class BatchedWorld:
         _lib.check(self.lib.t2d_check_events(self._ctx, _ptr(o.flags), _ptr(o.hit_index), _ptr(o.hit_segment), self._stream()))
         return o
 
+    def lidar_scan(self, n_beams: int = 500, max_range: float = 12.0) -> torch.Tensor:
+        """Single-line lidar of every scenario's ego (``SingleLineLidar._scan_obstacles``, sensor/lidar.py:128-221):
+        fp32 [N, n_beams] distances, ``inf`` where nothing is hit within ``max_range``.  Defaults are the
+        reference's (range 12 m, freq_detect / freq_scan = 5000 / 10 = 500 beams, lidar.py:35-50)."""
+        key = (int(n_beams), float(max_range))
+        cache = getattr(self, "_lidar", None)
+        if cache is None or cache[0] != key:
+            theta = np.linspace(0, 2 * np.pi, int(n_beams), endpoint=False)          # lidar.py:160
+            cs = torch.from_numpy(np.stack([np.cos(theta), np.sin(theta)], 1)).to(self.device)   # float64, host trig
+            scan = torch.empty((self.N, int(n_beams)), dtype=torch.float32, device=self.device)
+            self._lidar = cache = (key, cs.contiguous(), scan)
+        _lib.check(self.lib.t2d_lidar_scan(self._ctx, int(n_beams), float(max_range), _ptr(cache[1]), _ptr(cache[2]), self._stream()))
+        return cache[2]
+
     def reset(self, mask: torch.Tensor, pool: dict, pool_index: Optional[torch.Tensor] = None):
         """Re-initialise the scenarios with ``mask[n] != 0`` from row ``pool_index[n]`` (default n)
         of the pool arrays ``x, y, heading, speed[, vx, vy]`` [P, M] (``ScenarioManager.reset``,

@@ -309,3 +309,35 @@ def test_batched_env_with_targets_terminates_on_arrival(cuda_device):
     assert (terminated == (st == int(ScenarioStatus.COMPLETED))).all() and not (terminated & truncated).any()
     assert (reward[terminated] == 5.0).all() and (info["iou"][terminated] >= 0.95).all()
     env.close()
+
+
+@pytest.mark.parametrize("n_beams,max_range", [(360, 20.0), (500, 12.0), (37, 30.0)])
+def test_lidar_scan_matches_reference_restatement(cuda_device, n_beams, max_range):
+    """SingleLineLidar._scan_obstacles for every ego against the NumPy restatement (oracle/lidar.py): same hit / no-hit
+    pattern and distances (the device works in fp64 on the fp32 poses)."""
+    import torch
+
+    from oracle import lidar as OL
+    from tactics2d_b200 import BatchedWorld, synthetic
+    from tactics2d_b200.sensor import SingleLineLidar
+
+    scene = synthetic.with_inactive(synthetic.config4(40, 32, seed=41, size=60.0, segments=synthetic.grid_wall_segments(60.0, 30.0, 14.0)),
+                                    0.1, seed=3)
+    scene.type_id[:, 0] = np.where(scene.type_id[:, 0] == 255, 2, scene.type_id[:, 0])   # keep most egos
+    scene.type_id[3, 0] = 255                                                           # ... but one scenario has none
+    w = BatchedWorld(40, 32, scene.table, device=cuda_device)
+    w.set_map(scene.segments, scene.bounds)
+    w.set_state(scene.x, scene.y, scene.heading, scene.speed, vx=scene.vx, vy=scene.vy, type_id=scene.type_id)
+    lidar = SingleLineLidar(perception_range=max_range, freq_scan=1.0, freq_detect=float(n_beams))
+    assert lidar.point_density == n_beams
+    got = lidar.scan(w).cpu().numpy().astype(np.float64)
+    ref = OL.scan_world(scene.x.astype(np.float64), scene.y.astype(np.float64), scene.heading.astype(np.float64), scene.type_id,
+                        scene.table.as_oracle_table(), scene.segments, n_beams, max_range)
+    assert got.shape == ref.shape == (40, n_beams)
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    hit = np.isfinite(ref)
+    assert hit.mean() > 0.2 and np.isinf(got[3]).all()
+    assert np.abs(got[hit] - ref[hit]).max() < 2e-6 * max_range + 1e-6   # fp32 output rounding only
+    pts = lidar.get_points(w)
+    assert pts.shape == (40, n_beams, 2) and torch.isfinite(pts[torch.from_numpy(hit).to(cuda_device)]).all()
+    w.close()
