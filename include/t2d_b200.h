@@ -145,6 +145,16 @@ int t2d_bind_state(t2d_ctx* ctx, float* x, float* y, float* heading, float* spee
 int t2d_step(t2d_ctx* ctx, const float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
              uint8_t* scn_status, uint8_t* done, void* stream);
 
+/* The same tick for a caller whose buffers live in HOST memory - what a ctypes / numpy binding of the reference's
+ * env.step(action) -> (..., terminated, truncated, info["status"]) would hand over (envs/parking.py:444-468).
+ * action_host: [N, M, 2] fp32 (pinned memory recommended), scn_status_host / done_host: [N] uint8 in host memory
+ * (either may be NULL); flags / hit_index / hit_segment stay DEVICE arrays as in t2d_step (any may be NULL).
+ * The library stages the actions in chunks of whole scenarios on its own copy stream so that the host->device copy of
+ * one chunk runs under the kernel of the previous one, reads status + done back in one device->host copy and
+ * synchronises `stream` before returning: the host arrays are valid on return. */
+int t2d_step_host(t2d_ctx* ctx, const float* action_host, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
+                  uint8_t* scn_status_host, uint8_t* done_host, void* stream);
+
 /* The detectors alone on the bound poses (x, y, heading); no physics, no step counting. */
 int t2d_check_events(t2d_ctx* ctx, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, void* stream);
 

@@ -42,6 +42,7 @@ SYMBOLS = {
     "t2d_set_map": (C.c_int, [_P, _P, C.c_int, _P, C.c_float]),
     "t2d_bind_state": (C.c_int, [_P] + [_P] * 8),
     "t2d_step": (C.c_int, [_P] + [_P] * 7),
+    "t2d_step_host": (C.c_int, [_P] + [_P] * 7),
     "t2d_check_events": (C.c_int, [_P] + [_P] * 4),
     "t2d_set_goal": (C.c_int, [_P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "t2d_reset": (C.c_int, [_P, _P, _P, C.c_int] + [_P] * 7),

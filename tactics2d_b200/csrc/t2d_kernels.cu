@@ -1094,6 +1094,14 @@ struct t2d_ctx {
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
   int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // t2d_step_host: device staging for the host-resident action / status / done, the copy stream and its events
+  static constexpr int MAX_HOST_CHUNKS = 8;
+  float* hs_action = nullptr;          // [N][M][2]
+  uint8_t* hs_out = nullptr;           // [2][N] status, done
+  uint8_t* hs_out_pinned = nullptr;    // pinned host mirror of hs_out
+  cudaStream_t hs_copy = nullptr;
+  cudaEvent_t hs_begin = nullptr, hs_chunk[MAX_HOST_CHUNKS] = {};
+  int host_chunks = 0;                 // 0 = pick from the batch size
 };
 
 extern "C" {
@@ -1133,6 +1141,7 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   }
   c->ppl = ppl;
   if (const char* e = getenv("T2D_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("T2D_HOST_CHUNKS")) c->host_chunks = std::max(0, std::min(atoi(e), (int)t2d_ctx::MAX_HOST_CHUNKS));
   int g = 1;
   while (g * ppl < m_participants) g <<= 1;
   c->G = g;
@@ -1151,6 +1160,13 @@ int t2d_destroy(t2d_ctx* c) {
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_map) cudaFree(c->d_map);
   if (c->d_fine) cudaFree(c->d_fine);
+  if (c->hs_action) cudaFree(c->hs_action);
+  if (c->hs_out) cudaFree(c->hs_out);
+  if (c->hs_out_pinned) cudaFreeHost(c->hs_out_pinned);
+  if (c->hs_begin) cudaEventDestroy(c->hs_begin);
+  for (cudaEvent_t e : c->hs_chunk)
+    if (e) cudaEventDestroy(e);
+  if (c->hs_copy) cudaStreamDestroy(c->hs_copy);
   delete c;
   return T2D_OK;
 }
@@ -1346,22 +1362,27 @@ int t2d_bind_state(t2d_ctx* c, float* x, float* y, float* heading, float* speed,
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Launches K1 over the scenarios [first, first + count) of the bound state; the per-participant / per-scenario
+// pointers passed in (action, flags, ..., done) address scenario `first` already.
 static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
-                       uint8_t* scn_status, uint8_t* done, void* stream, int do_physics) {
+                       uint8_t* scn_status, uint8_t* done, void* stream, int do_physics, int first = 0, int count = -1) {
   if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
   if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
   if (!c->d_table || c->n_types == 0) return fail(T2D_E_STATE, "type table not set: call t2d_set_type_table first");
   if (do_physics && !action) return fail(T2D_E_INVALID, "action is NULL");
   CUDA_TRY(cudaSetDevice(c->device));
+  if (count < 0) count = c->N - first;
+  if (first < 0 || count <= 0 || first + count > c->N) return fail(T2D_E_INVALID, "scenario range out of bounds");
+  const size_t p0 = (size_t)first * c->M;
   StepArgs A{};
-  A.x = c->x; A.y = c->y; A.h = c->h; A.v = c->v; A.vx = c->vx; A.vy = c->vy;
-  A.type_id = c->type_id; A.step_count = c->step_count;
+  A.x = c->x + p0; A.y = c->y + p0; A.h = c->h + p0; A.v = c->v + p0; A.vx = c->vx + p0; A.vy = c->vy + p0;
+  A.type_id = c->type_id + p0; A.step_count = c->step_count + first;
   A.action = action; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
   A.scn_status = scn_status; A.done = done;
   A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine; A.mh = c->mh;
   A.map_in_smem = (c->d_map && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
   A.table = c->d_table; A.n_types = c->n_types;
-  A.N = c->N; A.M = c->M; A.G = c->G;
+  A.N = count; A.M = c->M; A.G = c->G;
   const int delta_t = std::min(c->cfg.delta_t_ms, c->cfg.interval_ms);
   A.n_steps = c->cfg.interval_ms / delta_t;                       // single_track_kinematics.py:129
   A.dt = (float)((double)delta_t / 1000.0);                      // :128
@@ -1381,11 +1402,13 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
 
   A.rb_max = c->rb_max;
   A.dbg_clock = c->dbg_clock;
-  A.goal_target = c->goal_target; A.goal_iou = c->goal_iou; A.goal_last_pose = c->goal_last_pose;
-  A.goal_noact_count = c->goal_noact_count; A.goal_threshold = c->goal_threshold; A.goal_noact_max = c->goal_noact_max;
+  A.goal_target = c->goal_target ? c->goal_target + 5 * (size_t)first : nullptr;
+  A.goal_iou = c->goal_iou ? c->goal_iou + first : nullptr;
+  A.goal_last_pose = c->goal_last_pose ? c->goal_last_pose + 4 * (size_t)first : nullptr;
+  A.goal_noact_count = c->goal_noact_count ? c->goal_noact_count + first : nullptr; A.goal_threshold = c->goal_threshold; A.goal_noact_max = c->goal_noact_max;
   const int table_bytes = ((c->n_types * (int)sizeof(Params) + 15) / 16) * 16;
   const int spw = 32 / c->G;
-  const long long tiles = ((long long)c->N + spw - 1) / spw;
+  const long long tiles = ((long long)count + spw - 1) / spw;
   // warps per CTA: the largest of 8 / 4 / 2 that still leaves >= 6 CTAs per SM (small batches balance
   // across the 148 SMs only with small CTAs; large batches amortise the map staging over more warps)
   int wpc = 2;
@@ -1474,6 +1497,50 @@ int t2d_debug_set_clock_buffer(t2d_ctx* c, long long* device_buffer) {
 int t2d_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, uint8_t* scn_status,
              uint8_t* done, void* stream) {
   return launch_step(c, action, flags, hit_index, hit_segment, scn_status, done, stream, 1);
+}
+
+int t2d_step_host(t2d_ctx* c, const float* action_host, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
+                  uint8_t* scn_status_host, uint8_t* done_host, void* stream) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!action_host) return fail(T2D_E_INVALID, "action is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int N = c->N, M = c->M;
+  if (!c->hs_action) {
+    CUDA_TRY(cudaMalloc(&c->hs_action, (size_t)N * M * 2 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->hs_out, 2 * (size_t)N));
+    CUDA_TRY(cudaMallocHost(&c->hs_out_pinned, 2 * (size_t)N));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->hs_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->hs_begin, cudaEventDisableTiming));
+    for (cudaEvent_t& e : c->hs_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // Chunks of whole scenarios: the copy of chunk k + 1 (copy engine, own stream) runs under the kernel of chunk k.
+  // A chunk keeps 16-byte alignment of every per-participant array (first * M a multiple of 16) and is at least
+  // 256 KiB of actions - below that the PCIe latency, not the bandwidth, is what a split would pay twice.
+  int chunks = c->host_chunks;
+  if (chunks <= 0) chunks = (int)std::min<long long>(4, std::max<long long>(1, (long long)N * M * 8 / (256 << 10)));
+  int per = (N + chunks - 1) / chunks;
+  per = (per + 15) & ~15;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaEventRecord(c->hs_begin, s));              // the copies follow whatever the caller queued on `stream`
+  CUDA_TRY(cudaStreamWaitEvent(c->hs_copy, c->hs_begin, 0));
+  int k = 0;
+  for (int first = 0; first < N; first += per, ++k) {
+    const int count = std::min(per, N - first);
+    const size_t a0 = (size_t)first * M * 2;
+    CUDA_TRY(cudaMemcpyAsync(c->hs_action + a0, action_host + a0, (size_t)count * M * 2 * sizeof(float), cudaMemcpyHostToDevice,
+                             c->hs_copy));
+    CUDA_TRY(cudaEventRecord(c->hs_chunk[k], c->hs_copy));
+    CUDA_TRY(cudaStreamWaitEvent(s, c->hs_chunk[k], 0));
+    const size_t p0 = (size_t)first * M;
+    if (int r = launch_step(c, c->hs_action + a0, flags ? flags + p0 : nullptr, hit_index ? hit_index + p0 : nullptr,
+                            hit_segment ? hit_segment + p0 : nullptr, c->hs_out + first, c->hs_out + N + first, stream, 1, first, count))
+      return r;
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->hs_out_pinned, c->hs_out, 2 * (size_t)N, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (scn_status_host) memcpy(scn_status_host, c->hs_out_pinned, (size_t)N);
+  if (done_host) memcpy(done_host, c->hs_out_pinned + N, (size_t)N);
+  return T2D_OK;
 }
 
 int t2d_check_events(t2d_ctx* c, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, void* stream) {

@@ -193,6 +193,30 @@ class BatchedWorld:
         self.frame += self.interval
         return o
 
+    @property
+    def result(self) -> StepResult:
+        """The device-side output arrays of the last ``step`` / ``step_host`` / ``check_events``."""
+        return self._out
+
+    def step_host(self, action):
+        """One tick for a host-side caller: ``action`` is a float32 ``[N, M, 2]`` NumPy array or CPU tensor (pinned
+        memory avoids the driver's staging copy).  Returns ``(done, status)`` as uint8 NumPy arrays [N], valid on
+        return; the per-participant flags / hit indices stay on the device in ``self.result`` (whose ``status`` /
+        ``done`` tensors this call does not touch).  The copies are
+        inside the call (``t2d_step_host``): chunked host->device copy overlapped with the kernel, one
+        device->host read-back, one stream synchronisation."""
+        a = action if isinstance(action, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action, dtype=np.float32))
+        if a.device.type != "cpu" or a.dtype != torch.float32 or tuple(a.shape) != (self.N, self.M, 2) or not a.is_contiguous():
+            raise ValueError(f"action must be a contiguous float32 host array [{self.N}, {self.M}, 2]")
+        hb = getattr(self, "_host_out", None)
+        if hb is None:
+            hb = self._host_out = (np.empty(self.N, np.uint8), np.empty(self.N, np.uint8))
+        o = self._out
+        _lib.check(self.lib.t2d_step_host(self._ctx, a.data_ptr(), _ptr(o.flags), _ptr(o.hit_index), _ptr(o.hit_segment),
+                                          hb[1].ctypes.data, hb[0].ctypes.data, self._stream()))
+        self.frame += self.interval
+        return hb[0], hb[1]
+
     def check_events(self) -> StepResult:
         """The detectors on the current poses, no physics (``EventBase.update``)."""
         o = self._out

@@ -354,3 +354,35 @@ def test_map_too_large_for_shared_memory_uses_global_path(cuda_device):
     scene.segments = seg
     stats = _teacher_forced(scene, cuda_device, 2, seed=16, any_participant=True)
     assert stats["static"] > 0
+
+
+@pytest.mark.parametrize("n,m,chunks", [(256, 64, 0), (100, 7, 3), (50, 128, 2), (4096, 64, 0)])
+def test_step_host_equals_step(cuda_device, monkeypatch, n, m, chunks):
+    """t2d_step_host (host action in, host done / status out, chunked copy under the kernel) is the same tick as
+    t2d_step on device buffers: state, flags, hit indices, status and done bit-identical over a rollout that
+    carries collisions and time-outs, for chunk splits that do and do not divide N."""
+    import torch
+
+    from tactics2d_b200 import synthetic
+
+    monkeypatch.setenv("T2D_HOST_CHUNKS", str(chunks))
+    scene = synthetic.config2(n, m, seed=77)
+    a = _world(scene, cuda_device, max_step=4)
+    b = _world(scene, cuda_device, max_step=4)
+    seen_done = 0
+    for t in range(6):
+        act = synthetic.random_actions(4200 + t, (n, m))
+        ra = a.step(torch.from_numpy(act).to(cuda_device))
+        host = torch.from_numpy(act).pin_memory() if t % 2 == 0 else act          # pinned and pageable callers
+        done, status = b.step_host(host)
+        torch.cuda.synchronize()
+        sa, sb = a.state_numpy(), b.state_numpy()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k], equal_nan=True), (t, k)
+        assert np.array_equal(ra.flags.cpu().numpy(), b.result.flags.cpu().numpy())
+        assert np.array_equal(ra.hit_index.cpu().numpy(), b.result.hit_index.cpu().numpy())
+        assert np.array_equal(ra.hit_segment.cpu().numpy(), b.result.hit_segment.cpu().numpy())
+        assert np.array_equal(ra.status.cpu().numpy(), status)
+        assert np.array_equal(ra.done.cpu().numpy(), done)
+        seen_done += int(done.sum())
+    assert seen_done > 0
