@@ -1514,23 +1514,29 @@ int t2d_step_host(t2d_ctx* c, const float* action_host, uint8_t* flags, int16_t*
     for (cudaEvent_t& e : c->hs_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   // Chunks of whole scenarios: the copy of chunk k + 1 (copy engine, own stream) runs under the kernel of chunk k.
-  // A chunk keeps 16-byte alignment of every per-participant array (first * M a multiple of 16) and is at least
-  // 256 KiB of actions - below that the PCIe latency, not the bandwidth, is what a split would pay twice.
+  // Measured on B200 (profiles/r01_e2e_probe.txt): at 4096 x 64 the 2 MiB upload is ~50 us against a 21 us kernel
+  // whose duration is one tile's lifetime whatever the batch, so splitting only adds ~3.5 us per chunk; it pays
+  // once a chunk alone fills the GPU, i.e. from ~1 M participants (8 MiB of actions) per chunk upwards.
   int chunks = c->host_chunks;
-  if (chunks <= 0) chunks = (int)std::min<long long>(4, std::max<long long>(1, (long long)N * M * 8 / (256 << 10)));
+  if (chunks <= 0) chunks = (int)std::min<long long>(t2d_ctx::MAX_HOST_CHUNKS, std::max<long long>(1, (long long)N * M / (1 << 20)));
   int per = (N + chunks - 1) / chunks;
   per = (per + 15) & ~15;
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaEventRecord(c->hs_begin, s));              // the copies follow whatever the caller queued on `stream`
-  CUDA_TRY(cudaStreamWaitEvent(c->hs_copy, c->hs_begin, 0));
+  const bool split = per < N;   // a single chunk needs no second stream
+  if (split) {
+    CUDA_TRY(cudaEventRecord(c->hs_begin, s));            // the copies follow whatever the caller queued on `stream`
+    CUDA_TRY(cudaStreamWaitEvent(c->hs_copy, c->hs_begin, 0));
+  }
   int k = 0;
   for (int first = 0; first < N; first += per, ++k) {
     const int count = std::min(per, N - first);
     const size_t a0 = (size_t)first * M * 2;
     CUDA_TRY(cudaMemcpyAsync(c->hs_action + a0, action_host + a0, (size_t)count * M * 2 * sizeof(float), cudaMemcpyHostToDevice,
-                             c->hs_copy));
-    CUDA_TRY(cudaEventRecord(c->hs_chunk[k], c->hs_copy));
-    CUDA_TRY(cudaStreamWaitEvent(s, c->hs_chunk[k], 0));
+                             split ? c->hs_copy : s));
+    if (split) {
+      CUDA_TRY(cudaEventRecord(c->hs_chunk[k], c->hs_copy));
+      CUDA_TRY(cudaStreamWaitEvent(s, c->hs_chunk[k], 0));
+    }
     const size_t p0 = (size_t)first * M;
     if (int r = launch_step(c, c->hs_action + a0, flags ? flags + p0 : nullptr, hit_index ? hit_index + p0 : nullptr,
                             hit_segment ? hit_segment + p0 : nullptr, c->hs_out + first, c->hs_out + N + first, stream, 1, first, count))
