@@ -14,6 +14,8 @@
  *                                                         vehicle.py:111-118,179-221, cyclist.py:76-94, pedestrian.py:70-88
  *   t2d_set_map          StaticCollision.reset / OutBound.reset
  *                                                         tactics2d/traffic/event_detection/collision.py:45-46, out_bound.py:50-65
+ *   t2d_bind_wheel_state the omega_wf / omega_wr arguments of SingleTrackDrift.step
+ *                                                         tactics2d/physics/single_track_drift.py:467-499
  *   t2d_bind_state       Trajectory.add_state / current state
  *                                                         tactics2d/participant/trajectory/trajectory.py:115-149
  *   t2d_step             ScenarioManager.update + check_status
@@ -26,6 +28,13 @@
  *                        TimeExceed.update                tactics2d/traffic/event_detection/time_exceed.py:26-33
  *   t2d_set_goal         Arrival.update / NoAction.update  tactics2d/traffic/event_detection/arrival.py:32-47, no_action.py:32-53
  *   t2d_lidar_scan       SingleLineLidar._scan_obstacles   tactics2d/sensor/lidar.py:128-221
+ *   t2d_set_controllers  IDMController / AccelerationController / PurePursuitController objects
+ *                                                         tactics2d/controller/idm_controller.py:33-58,
+ *                                                         acceleration_controller.py:33-80, pure_pursuit_controller.py:26-49
+ *   t2d_set_paths        the `waypoints` LineString of PurePursuitController.step   pure_pursuit_controller.py:76,92
+ *   t2d_control          ControllerBase.step for every controlled participant
+ *                                                         idm_controller.py:59-141, acceleration_controller.py:82-145,
+ *                                                         pure_pursuit_controller.py:51-98
  *   t2d_check_events     the same detectors on caller-supplied poses (no physics)
  *   t2d_reset            ScenarioManager.reset / ParticipantBase.reset
  *                                                         tactics2d/envs/parking.py:397-441, participant_base.py:236-246
@@ -68,6 +77,7 @@ extern "C" {
 #define T2D_MODEL_POINTMASS_NEWTON 2 /* PointMass(backend="newton") */
 #define T2D_MODEL_POINTMASS_EULER 3  /* PointMass(backend="euler")  */
 #define T2D_MODEL_STATIC 4           /* no motion (Obstacle, obstacle.py:14-19) */
+#define T2D_MODEL_DRIFT 5            /* SingleTrackDrift (built-in tyre); needs t2d_bind_wheel_state */
 
 /* collision shape ids (t2d_type_params.shape) */
 #define T2D_SHAPE_OBB 0    /* Vehicle / Cyclist / Other bounding box, vehicle.py:132-142 */
@@ -117,6 +127,8 @@ typedef struct t2d_type_params {
   float mass, mass_height, mu, I_z, cf, cr; /* SingleTrackDynamics only */
   int32_t model;                            /* T2D_MODEL_* */
   int32_t shape;                            /* T2D_SHAPE_* */
+  float wheel_radius, T_sb, T_se, I_yw;     /* SingleTrackDrift only (single_track_drift.py:98-107: 0.344, 0.76, 1, 1.7);
+                                               the drift model also reads lf, lr, mass, I_z and the three ranges */
 } t2d_type_params;
 
 int t2d_version(void);
@@ -137,6 +149,12 @@ int t2d_set_map(t2d_ctx* ctx, const float* segments, int n_seg, const float* bou
 /* DEVICE pointers, each [N, M] (step_count: [N]); read and written in place by t2d_step. */
 int t2d_bind_state(t2d_ctx* ctx, float* x, float* y, float* heading, float* speed, float* vx, float* vy,
                    const uint8_t* type_id, int32_t* step_count);
+
+/* SingleTrackDrift carries two more state variables per participant, the front / rear wheel angular speeds that
+ * SingleTrackDrift.step takes and returns (single_track_drift.py:467-499).  DEVICE pointers [N, M], read and written in
+ * place by t2d_step for participants whose type has model T2D_MODEL_DRIFT; required only when the type table holds
+ * such a row. */
+int t2d_bind_wheel_state(t2d_ctx* ctx, float* omega_front, float* omega_rear);
 
 /* One tick of all N scenarios.  action: [N, M, 2] fp32.  Outputs (any may be NULL):
  * flags [N, M] uint8, hit_index [N, M] int16 (lowest colliding participant or -1),
@@ -182,12 +200,54 @@ int t2d_reset(t2d_ctx* ctx, const uint8_t* mask, const int32_t* pool_index, int 
  * segments given to t2d_set_map and the pose rings of the other box-shaped participants. */
 int t2d_lidar_scan(t2d_ctx* ctx, int n_beams, float max_range, const double* beam_cos_sin, float* scan, void* stream);
 
+/* On-device NPC controllers (tactics2d/controller).  A controller row is one configured controller object; the fields
+ * are the reference's attribute names.  kind selects the law:
+ *   T2D_CTRL_IDM           IDMController.step               (steering 0; free flow, or car following when a leader is set)
+ *   T2D_CTRL_CRUISE        AccelerationController.step      (steering 0; cruise, or adaptive cruise with a leader)
+ *   T2D_CTRL_PURE_PURSUIT  PurePursuitController.step       (pure-pursuit steering on a path + the cruise laws) */
+#define T2D_CTRL_EXTERNAL 0 /* the caller's action is kept */
+#define T2D_CTRL_IDM 1
+#define T2D_CTRL_CRUISE 2
+#define T2D_CTRL_PURE_PURSUIT 3
+#define T2D_MAX_CONTROLLERS 64
+
+typedef struct t2d_controller_params {
+  int32_t kind; /* T2D_CTRL_* */
+  /* IDMController.__init__, idm_controller.py:33-58 */
+  float desired_speed, time_headway, min_spacing, max_acceleration, comfortable_deceleration, delta;
+  /* AccelerationController attributes, acceleration_controller.py:33-39 (after update_driving_style, :62-80) */
+  float target_speed, kp, accel_change_rate, delta_t, max_accel, min_accel, interval;
+  /* PurePursuitController: min_pre_aiming_distance, interval (pure_pursuit_controller.py:26-36), wheel_base (:76) */
+  float min_pre_aiming_distance, pp_interval, wheel_base;
+} t2d_controller_params;
+
+/* table: HOST array of n_rows (<= T2D_MAX_CONTROLLERS) rows, copied.  The rest are DEVICE arrays owned by the caller:
+ * ctrl_id [N, M] uint8 = row of the participant's controller (255, or a row of kind EXTERNAL: not controlled);
+ * lead_index [N, M] int16 = the participant's leading vehicle inside its scenario (`leading_state` / `front_state`),
+ * -1 for none (NULL: nobody has one); path_id [N, M] int16 = the pure-pursuit path, -1 for none (NULL allowed);
+ * last_accel [N, M] float = |acceleration| each participant applied on the previous tick (State.accel,
+ * participant/trajectory/state.py:171-185), read and rewritten by t2d_control; zero it before the first tick.
+ * table == NULL removes the controllers. */
+int t2d_set_controllers(t2d_ctx* ctx, const t2d_controller_params* table, int n_rows, const uint8_t* ctrl_id,
+                        const int16_t* lead_index, const int16_t* path_id, float* last_accel);
+
+/* Pure-pursuit paths: HOST arrays, copied.  xy [V][2] vertices of all paths back to back, offsets [n_paths + 1] (path p
+ * owns vertices offsets[p] .. offsets[p + 1] - 1, at least 2). */
+int t2d_set_paths(t2d_ctx* ctx, const float* xy, const int32_t* offsets, int n_paths);
+
+/* Overwrites action[n][m] = (accel, steer) ((steer, accel) with T2D_CFG_STEER_FIRST) of every controlled participant from
+ * the bound state, then stores |applied acceleration| of the WHOLE action buffer in last_accel (bicycles: the accel clipped
+ * to the type's range; point masses: |(ax, ay)|).  Call it after the external actions are in the buffer and before
+ * t2d_step.  action: DEVICE [N, M, 2] fp32. */
+int t2d_control(t2d_ctx* ctx, float* action, void* stream);
+
 /* Flat batch of `n` independent participants through ONE model (PhysicsModelBase.step):
  * state arrays are read and written in place; action [n, 2]; applied [n, 2] (may be NULL)
- * receives the clipped (accel, steer) the reference returns next to the State. */
+ * receives the clipped (accel, steer) the reference returns next to the State.  omega_front / omega_rear [n]: the wheel
+ * speeds of SingleTrackDrift.step (in / out); NULL for every other model. */
 int t2d_physics_step(int device, const t2d_type_params* params /*host*/, int interval_ms, int delta_t_ms, int n,
-                     float* x, float* y, float* heading, float* speed, float* vx, float* vy, const float* action,
-                     float* applied, void* stream);
+                     float* x, float* y, float* heading, float* speed, float* vx, float* vy, float* omega_front,
+                     float* omega_rear, const float* action, float* applied, void* stream);
 
 /* Diagnostics: device buffer int64[ceil(N / scenarios_per_warp)][10] that receives clock64() at the eight phase
  * boundaries of every warp tile of t2d_step (load, physics, pose, pair loop, pair drain, static, out-of-bound, end), the SM id and the warp's kernel-entry clock;

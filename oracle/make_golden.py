@@ -149,7 +149,150 @@ def main():
         vs_out.append(bool(ok))
     np.savez(os.path.join(OUT, "verify_state.npz"), inputs=np.array(vs_in),
              valid=np.array(vs_out))
+    controllers_golden(rng)
+    drift_golden(rng)
     print("golden vectors written to", os.path.normpath(OUT))
+
+
+def drift_golden(rng):
+    """SingleTrackDrift (single_track_drift.py:340-465): two consecutive steps per case (the second one consumes the
+    wheel speeds the first one returned), fp32-representable inputs."""
+    from tactics2d.participant.trajectory import State
+    from tactics2d.physics import SingleTrackDrift
+
+    n = 160
+    st = np.stack([rng.uniform(-200, 200, n), rng.uniform(-200, 200, n), rng.uniform(0, 2 * np.pi, n),
+                   rng.uniform(0.5, 30, n)], 1)
+    st[:12, 3] = rng.uniform(-0.09, 0.09, 12)               # the |v| < 0.1 kinematic branch
+    st[12:20, 3] = rng.uniform(-8, -0.5, 8)                 # reversing
+    act = np.stack([rng.uniform(-6, 4, n), rng.uniform(-0.6, 0.6, n)], 1)
+    act[20:24] = 0.0
+    act2 = np.stack([rng.uniform(-6, 4, n), rng.uniform(-0.6, 0.6, n)], 1)
+    st, act, act2 = (a.astype(np.float32).astype(np.float64) for a in (st, act, act2))
+    radius = 0.344
+    om = np.stack([st[:, 3] / radius * rng.uniform(0.9, 1.1, n), st[:, 3] / radius * rng.uniform(0.9, 1.1, n)], 1)
+    om = om.astype(np.float32).astype(np.float64)
+    out = dict(states=st, actions=act, actions2=act2, omega=om, lf=MEDIUM["lf"], lr=MEDIUM["lr"], mass=MEDIUM["mass"],
+               mass_height=MEDIUM["mass_height"], steer_range=RANGES["steer_range"], speed_range=RANGES["speed_range"],
+               accel_range=RANGES["accel_range"])
+    for name, kw in [("con", RANGES), ("unc", dict())]:
+        for interval, delta_t in [(100, 5), (9, 5), (50, 3)]:
+            m = SingleTrackDrift(lf=MEDIUM["lf"], lr=MEDIUM["lr"], mass=MEDIUM["mass"], mass_height=MEDIUM["mass_height"],
+                                 interval=interval, delta_t=delta_t, **kw)
+            rec = np.zeros((n, 2, 8))
+            for i in range(n):
+                s = State(0, x=st[i, 0], y=st[i, 1], heading=st[i, 2], speed=st[i, 3])
+                wf, wr = om[i]
+                for k, a in enumerate((act[i], act2[i])):
+                    s, wf, wr, a_c, d_c = m.step(s, wf, wr, a[0], a[1], interval)
+                    rec[i, k] = (s.x, s.y, s.heading, s.speed, wf, wr, a_c, d_c)
+            out[f"drift_{name}_{interval}_{delta_t}"] = rec
+    np.savez(os.path.join(OUT, "physics_drift.npz"), **out)
+
+
+def _shapely_stand_in():
+    """``tactics2d.controller`` imports ``shapely.geometry.{LineString, Point}`` (pure_pursuit_controller.py:8) and
+    uses exactly one method of them, ``LineString.interpolate`` (:92).  shapely is not installable in this image, so
+    the generator provides that one method (arc-length walk from the first vertex, clamped to the last) and nothing
+    else; every other line executed below is the reference's own."""
+    import types
+
+    class Point:
+        def __init__(self, x, y):
+            self.x, self.y = float(x), float(y)
+
+    class LineString:
+        def __init__(self, coords):
+            self.coords = [(float(a), float(b)) for a, b in coords]
+
+        def interpolate(self, d):
+            acc = 0.0
+            for (x0, y0), (x1, y1) in zip(self.coords[:-1], self.coords[1:]):
+                L = float(np.hypot(x1 - x0, y1 - y0))
+                if d <= acc + L and L > 0:
+                    t = (d - acc) / L
+                    return Point(x0 + t * (x1 - x0), y0 + t * (y1 - y0))
+                acc += L
+            return Point(*self.coords[-1])
+
+    shp, geo = types.ModuleType("shapely"), types.ModuleType("shapely.geometry")
+    geo.LineString, geo.Point = LineString, Point
+    shp.geometry = geo
+    sys.modules.setdefault("shapely", shp)
+    sys.modules.setdefault("shapely.geometry", geo)
+    return LineString
+
+
+def controllers_golden(rng):
+    """IDMController / AccelerationController / PurePursuitController outputs of the unmodified reference."""
+    LineString = _shapely_stand_in()
+    from tactics2d.controller.acceleration_controller import AccelerationController
+    from tactics2d.controller.idm_controller import IDMController
+    from tactics2d.controller.pure_pursuit_controller import PurePursuitController
+    from tactics2d.participant.trajectory import State
+
+    n = 256
+    ego = np.stack([rng.uniform(-100, 100, n), rng.uniform(-100, 100, n), rng.uniform(0, 2 * np.pi, n),
+                    rng.uniform(0, 25, n), rng.uniform(-4, 3, n)], 1)            # x y heading speed accel(signed)
+    ego[:8, 3] = 0.0
+    ego[8:16, 3] = rng.uniform(-3, 0, 8)                                         # reversing
+    gap = rng.uniform(0.5, 120, n)
+    gap[16:20] = 0.0                                                             # leader exactly on top (distance 0)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    lead = np.stack([ego[:, 0] + gap * np.cos(ang), ego[:, 1] + gap * np.sin(ang), rng.uniform(0, 2 * np.pi, n),
+                     rng.uniform(0, 25, n), rng.uniform(-4, 3, n)], 1)
+    lead[16:20, :2] = ego[16:20, :2]
+    # fp32-representable inputs: the device holds the state in fp32, so its outputs can be held to these vectors directly
+    ego, lead = ego.astype(np.float32).astype(np.float64), lead.astype(np.float32).astype(np.float64)
+
+    def st(row):
+        return State(0, x=row[0], y=row[1], heading=row[2], speed=row[3], accel=row[4])
+
+    out = dict(ego=ego, lead=lead)
+    idm_cfgs = [dict(), dict(desired_speed=0.0), dict(desired_speed=20.0, time_headway=1.0, min_spacing=1.0,
+                                                      max_acceleration=2.0, comfortable_deceleration=4.0, delta=4.0)]
+    for ci, cfg in enumerate(idm_cfgs):
+        c = IDMController(**cfg)
+        out[f"idm{ci}_free"] = np.array([c.step(st(e))[1] for e in ego], np.float64)
+        out[f"idm{ci}_follow"] = np.array([c.step(st(e), st(l))[1] for e, l in zip(ego, lead)], np.float64)
+    out["idm_cfgs"] = np.array([[IDMController(**c).__dict__[k] for k in
+                                 ("desired_speed", "time_headway", "min_spacing", "max_acceleration",
+                                  "comfortable_deceleration", "delta")] for c in idm_cfgs], np.float64)
+    acc_rows = []
+    for si, style in enumerate([None, -1.0, 0.3, 1.0]):
+        c = AccelerationController(target_speed=8.0)
+        if style is not None:
+            c.update_driving_style(style)
+        acc_rows.append([c.target_speed, float(c.kp), float(c.accel_change_rate), float(c.delta_t), float(c.max_accel),
+                         float(c.min_accel), float(c.interval)])
+        out[f"acc{si}_cruise"] = np.array([c.step(st(e))[1] for e in ego], np.float64)
+        out[f"acc{si}_follow"] = np.array([c.step(st(e), front_state=st(l))[1] for e, l in zip(ego, lead)], np.float64)
+    out["acc_cfgs"] = np.array(acc_rows, np.float64)
+    # pure pursuit: three paths, ego anywhere near them (the look-ahead is measured from the path's first vertex)
+    paths = [np.array([[0.0, 0.0], [30.0, 0.0], [60.0, 20.0], [60.0, 80.0]]),
+             np.array([[-50.0, -50.0], [-40.0, -50.0]]),                          # shorter than the look-ahead
+             np.stack([40 * np.cos(np.linspace(0, np.pi, 33)), 40 * np.sin(np.linspace(0, np.pi, 33))], 1)]
+    paths = [q.astype(np.float32).astype(np.float64) for q in paths]
+    pid = rng.integers(0, len(paths), n)
+    pp_rows, steer, accel = [], [], []
+    for si, (style, kw) in enumerate([(None, dict()), (0.5, dict(min_pre_aiming_distance=4.0, target_speed=12.0))]):
+        c = PurePursuitController(**kw)
+        if style is not None:
+            c.update_driving_style(style)
+        wb = 2.637 if si == 0 else 2.9
+        lc = c._longitudinal_control
+        pp_rows.append([lc.target_speed, float(lc.kp), float(lc.accel_change_rate), float(lc.delta_t), float(lc.max_accel),
+                        float(lc.min_accel), float(lc.interval), c.min_pre_aiming_distance, float(c.interval), wb])
+        r = [c.step(st(e), LineString(paths[k]), wheel_base=wb) for e, k in zip(ego, pid)]
+        r2 = [c.step(st(e), LineString(paths[k]), wheel_base=wb, front_state=st(l)) for e, k, l in zip(ego, pid, lead)]
+        out[f"pp{si}_steer"] = np.array([a[0] for a in r], np.float64)
+        out[f"pp{si}_accel"] = np.array([a[1] for a in r], np.float64)
+        out[f"pp{si}_accel_follow"] = np.array([a[1] for a in r2], np.float64)
+    out["pp_cfgs"] = np.array(pp_rows, np.float64)
+    out["path_id"] = pid.astype(np.int64)
+    for k, pth in enumerate(paths):
+        out[f"path{k}"] = pth
+    np.savez(os.path.join(OUT, "controllers.npz"), **out)
 
 
 if __name__ == "__main__":

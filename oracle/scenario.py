@@ -43,9 +43,16 @@ TABLE_FLOAT_FIELDS = ("half_len", "half_wid", "radius", "lf", "lr", "steer_lo", 
                       "mu", "I_z", "cf", "cr")
 
 
+DRIFT_FIELDS = ("wheel_radius", "T_sb", "T_se", "I_yw")
+DRIFT = 5
+
+
 def _gather(table, type_id):
     tid = np.where(type_id == INACTIVE, 0, type_id).astype(np.int64)
     out = {k: np.asarray(table[k], dtype=np.float64)[tid] for k in TABLE_FLOAT_FIELDS}
+    for k in DRIFT_FIELDS:      # SingleTrackDrift rows only; older tables do not carry them
+        if k in table:
+            out[k] = np.asarray(table[k], dtype=np.float64)[tid]
     out["model"] = np.asarray(table["model"])[tid]
     out["shape"] = np.asarray(table["shape"])[tid]
     return out
@@ -60,7 +67,8 @@ def physics_tick(state, type_id, action, table, interval=100, delta_t=5, steer_f
     a0 = np.asarray(action[..., 0], dtype=np.float64)
     a1 = np.asarray(action[..., 1], dtype=np.float64)
     acc, ste = (a1, a0) if steer_first else (a0, a1)
-    s = {k: np.asarray(state[k], dtype=np.float64) for k in ("x", "y", "heading", "speed", "vx", "vy")}
+    keys = ("x", "y", "heading", "speed", "vx", "vy") + tuple(k for k in ("omega_wf", "omega_wr") if k in state)
+    s = {k: np.asarray(state[k], dtype=np.float64) for k in keys}
     out = {k: s[k].copy() for k in s}
     active = type_id != INACTIVE
     rng = lambda a, b: (p[a], p[b])
@@ -80,6 +88,12 @@ def physics_tick(state, type_id, action, table, interval=100, delta_t=5, steer_f
                                p["mass"], p["mass_height"], p["mu"], p["I_z"], p["cf"], p["cr"],
                                rng("steer_lo", "steer_hi"), rng("speed_lo", "speed_hi"),
                                rng("accel_lo", "accel_hi"), interval, delta_t))
+    m = active & (p["model"] == DRIFT)
+    if m.any():     # wheel speeds travel in state["omega_wf"], state["omega_wr"] (single_track_drift.py:467-499)
+        put(m, P.step_drift(s["x"], s["y"], s["heading"], s["speed"], s["omega_wf"], s["omega_wr"], acc, ste, p["lf"], p["lr"],
+                            p["mass"], p["wheel_radius"], p["T_sb"], p["T_se"], p["I_z"], p["I_yw"],
+                            rng("steer_lo", "steer_hi"), rng("speed_lo", "speed_hi"), rng("accel_lo", "accel_hi"),
+                            interval, delta_t))
     m = active & (p["model"] == POINTMASS_NEWTON)
     if m.any():
         put(m, P.step_pointmass_newton(s["x"], s["y"], s["vx"], s["vy"], a0, a1,

@@ -27,7 +27,15 @@ class TypeParamsC(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "half_len", "half_wid", "radius", "lf", "lr", "steer_lo", "steer_hi", "speed_lo", "speed_hi",
         "accel_lo", "accel_hi", "mass", "mass_height", "mu", "I_z", "cf", "cr")] + [
-        ("model", C.c_int32), ("shape", C.c_int32)]
+        ("model", C.c_int32), ("shape", C.c_int32)] + [(n, C.c_float) for n in ("wheel_radius", "T_sb", "T_se", "I_yw")]
+
+
+class ControllerParamsC(C.Structure):
+    """``t2d_controller_params``: one configured controller object."""
+    _fields_ = [("kind", C.c_int32)] + [(n, C.c_float) for n in (
+        "desired_speed", "time_headway", "min_spacing", "max_acceleration", "comfortable_deceleration", "delta",
+        "target_speed", "kp", "accel_change_rate", "delta_t", "max_accel", "min_accel", "interval",
+        "min_pre_aiming_distance", "pp_interval", "wheel_base")]
 
 
 # name -> (restype, argtypes); every symbol include/t2d_b200.h declares
@@ -47,7 +55,11 @@ SYMBOLS = {
     "t2d_set_goal": (C.c_int, [_P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "t2d_reset": (C.c_int, [_P, _P, _P, C.c_int] + [_P] * 7),
     "t2d_lidar_scan": (C.c_int, [_P, C.c_int, C.c_float, _P, _P, _P]),
-    "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 9),
+    "t2d_set_controllers": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
+    "t2d_set_paths": (C.c_int, [_P, _P, _P, C.c_int]),
+    "t2d_control": (C.c_int, [_P, _P, _P]),
+    "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 11),
+    "t2d_bind_wheel_state": (C.c_int, [_P, _P, _P]),
     "t2d_debug_set_clock_buffer": (C.c_int, [_P, _P]),
     "t2d_launch_count": (C.c_int64, []),
 }

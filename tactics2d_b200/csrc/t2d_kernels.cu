@@ -80,6 +80,7 @@ struct StepArgs {
   float goal_threshold;
   int goal_noact_max;
   long long* dbg_clock;            // optional [n_tiles][8] phase time stamps (T2D_DEBUG_CLOCK); nullptr in production
+  float *wheel_f, *wheel_r;        // [N][M] wheel angular speeds of the SingleTrackDrift participants, or nullptr
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -186,6 +187,8 @@ __device__ __noinline__ void kin1_step(KinIO<1>& io, const Params& p, int n_step
 __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem, double interval) {
   if (p.model == MODEL_DYNAMICS) {
     dynamics_step(io, p, n_steps, dt);
+  } else if (p.model == MODEL_DRIFT) {
+    drift_step(io, p, n_steps, dt, dt_rem);
   } else if (p.model == MODEL_POINTMASS_NEWTON) {
     pointmass_newton_step(io, p, interval);
   } else if (p.model == MODEL_POINTMASS_EULER) {
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
         const Params& p = s_table[tidv[i] < A.n_types ? tidv[i] : 0];
-        if (p.model <= MODEL_DYNAMICS) { float t = a0[i]; a0[i] = a1[i]; a1[i] = t; }
+        if (p.model <= MODEL_DYNAMICS || p.model == MODEL_DRIFT) { float t = a0[i]; a0[i] = a1[i]; a1[i] = t; }
       }
     }
 
@@ -605,7 +608,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
             io.x = sx[i]; io.y = sy[i]; io.h = shd[i]; io.v = sv[i]; io.vx = svx[i]; io.vy = svy[i];
             io.a0 = a0[i]; io.a1 = a1[i];
             io.ch = 1.0f; io.sh = 0.0f;
+            const bool drift = pp[i]->model == MODEL_DRIFT;
+            if (drift) { io.w0 = A.wheel_f[idx0 + i]; io.w1 = A.wheel_r[idx0 + i]; }
             other_model_step(io, *pp[i], A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
+            if (drift) { A.wheel_f[idx0 + i] = io.w0; A.wheel_r[idx0 + i] = io.w1; }
             sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
             ch[i] = io.ch; sh[i] = io.sh;
           } else {
@@ -884,6 +890,7 @@ __global__ void t2d_reset_kernel(const __grid_constant__ ResetArgs A) {
 struct PhysArgs {
   Params p;
   float *x, *y, *h, *v, *vx, *vy;
+  float *wheel_f, *wheel_r;
   const float* action;
   float* applied;
   int n, n_steps;
@@ -906,7 +913,10 @@ __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant_
       io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = A.vx[i]; io.vy = A.vy[i];
       io.a0 = A.action[2 * i]; io.a1 = A.action[2 * i + 1];
       io.ch = 1.0f; io.sh = 0.0f;
+      const bool drift = A.p.model == MODEL_DRIFT;
+      if (drift) { io.w0 = A.wheel_f[i]; io.w1 = A.wheel_r[i]; }
       other_model_step(io, A.p, A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
+      if (drift) { A.wheel_f[i] = io.w0; A.wheel_r[i] = io.w1; }
       A.x[i] = io.x; A.y[i] = io.y; A.h[i] = io.h; A.v[i] = io.v; A.vx[i] = io.vx; A.vy[i] = io.vy;
       if (A.applied) { A.applied[2 * i] = io.a0; A.applied[2 * i + 1] = io.a1; }
     }
@@ -1044,6 +1054,157 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32) t2d_lidar_kernel(const __gri
   }
 }
 
+// ============================================================================ K5: NPC controllers
+// One warp per scenario; lane l owns participants l, l + 32, ... .  fp64 on the fp32 state (a few dozen flops per
+// participant: the kernel is bound by its ~30 B / participant of HBM traffic).  All reads of last_accel (own and the
+// leader's, previous tick) happen before the warp barrier, all writes (this tick) after it.
+struct PathVertex { double x, y, cum, len; };   // vertex, arc length up to it, length of the segment that starts here
+
+struct CtrlArgs {
+  const float *x, *y, *h, *v;
+  const uint8_t* type_id;
+  const Params* table;
+  int n_types;
+  const t2d_controller_params* ctab;
+  int n_ctrl;
+  const uint8_t* ctrl_id;
+  const int16_t* lead;
+  const int16_t* path_id;
+  const PathVertex* path_v;
+  const int* path_off;
+  int n_paths;
+  float* last_accel;
+  float* action;
+  int N, M, steer_first;
+};
+
+__device__ __forceinline__ double clip_np(double v, double lo, double hi) {   // np.clip: NaN propagates
+  return v != v ? v : fmin(fmax(v, lo), hi);
+}
+
+// acceleration_controller.py:82-130: cruise, or adaptive cruise when a leader is given
+__device__ double longitudinal_law(const t2d_controller_params& p, double v, double x, double y, double a_last, bool has_lead,
+                                   double vl, double xl, double yl, double al) {
+  const double kp = (double)p.kp;
+  double a;
+  if (has_lead) {
+    const double d_front = hypot(x - xl, y - yl);                                            // :114
+    const double d_target = clip_np(v * (double)p.interval + 5.0, 7.0, 80.0);                // :115-118, :42-45
+    const double rel_speed = vl - v;                                                         // :120
+    const double rel_target_speed = (d_target - d_front) / kp;                               // :121
+    const double rel_accel = (rel_target_speed - rel_speed) / kp;                            // :122
+    a = al - rel_accel;                                                                      // :124
+  } else {
+    a = ((double)p.target_speed - v) / kp;                                                   // :94
+  }
+  const double w = (double)p.accel_change_rate * (double)p.delta_t;
+  a = clip_np(a, a_last - w, a_last + w);                                                    // :95-99, :126-130
+  return clip_np(a, (double)p.min_accel, (double)p.max_accel);
+}
+
+// idm_controller.py:59-141
+__device__ double idm_law(const t2d_controller_params& p, double v, double x, double y, bool has_lead, double vl, double xl,
+                          double yl) {
+  const double vd = (double)p.desired_speed, am = (double)p.max_acceleration, b = (double)p.comfortable_deceleration;
+  double a;
+  if (!has_lead) {
+    a = vd > 0.0 ? am * (1.0 - pow(v / vd, (double)p.delta)) : (v > 0.0 ? -b : 0.0);         // :74-82
+  } else {
+    const double dist = hypot(xl - x, yl - y);                                               // :107-109
+    const double dv = vl - v;                                                                // :112
+    double s_star = (double)p.min_spacing + v * (double)p.time_headway + (v * dv) / (2.0 * sqrt(am * b));   // :116-120
+    s_star = fmax(s_star, (double)p.min_spacing);                                            // :121
+    if (dist > 0.0) {
+      const double ratio = vd > 0.0 ? pow(v / vd, (double)p.delta) : (v > 0.0 ? 1.0 : 0.0);  // :127-130
+      const double q = s_star / dist;
+      a = am * (1.0 - ratio - q * q);                                                        // :132-134
+    } else {
+      a = -b;                                                                                // :137
+    }
+  }
+  return clip_np(a, -b, am);                                                                 // :89
+}
+
+// pure_pursuit_controller.py:51-74,90-92; LineString.interpolate = arc-length walk from the first vertex
+__device__ double pure_pursuit_law(const t2d_controller_params& p, const PathVertex* pv, int n_vert, double v, double x, double y,
+                                   double heading) {
+  const double d = fmax(v * (double)p.pp_interval, (double)p.min_pre_aiming_distance);     // :90-91
+  double px = pv[n_vert - 1].x, py = pv[n_vert - 1].y;
+  for (int i = 0; i + 1 < n_vert; ++i) {
+    const PathVertex q = pv[i];
+    if (d <= q.cum + q.len && q.len > 0.0) {
+      const double t = (d - q.cum) / q.len;
+      px = q.x + t * (pv[i + 1].x - q.x);
+      py = q.y + t * (pv[i + 1].y - q.y);
+      break;
+    }
+  }
+  const double ang = atan2(py - y, px - x);                                                 // :62-64
+  const double dist = hypot(py - y, px - x);                                                // :65-67
+  return atan(2.0 * (double)p.wheel_base * sin(ang - heading) / dist);                      // :68-70
+}
+
+__global__ void __launch_bounds__(128) t2d_control_kernel(const __grid_constant__ CtrlArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < A.N; n += warps) {
+    const size_t base = (size_t)n * A.M;
+    float2 out[4];
+    float mag[4];
+    bool ctl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = lane + 32 * j;
+      ctl[j] = false;
+      mag[j] = 0.0f;
+      out[j] = make_float2(0.0f, 0.0f);
+      if (m >= A.M) continue;
+      const int tid = A.type_id[base + m];
+      if (tid >= A.n_types) continue;                  // inactive slot
+      const Params& tp = A.table[tid];
+      out[j] = reinterpret_cast<const float2*>(A.action)[base + m];
+      const int cid = A.ctrl_id[base + m];
+      if (cid < A.n_ctrl && A.ctab[cid].kind != T2D_CTRL_EXTERNAL) {
+        const t2d_controller_params& p = A.ctab[cid];
+        const double x = A.x[base + m], y = A.y[base + m], v = A.v[base + m];
+        const int li = A.lead ? (int)A.lead[base + m] : -1;
+        const bool has = li >= 0 && li < A.M && li != m && A.type_id[base + li] < A.n_types;
+        double xl = 0.0, yl = 0.0, vl = 0.0, al = 0.0;
+        if (has) {
+          xl = A.x[base + li]; yl = A.y[base + li]; vl = A.v[base + li]; al = A.last_accel[base + li];
+        }
+        double acc, steer = 0.0;
+        if (p.kind == T2D_CTRL_IDM) {
+          acc = idm_law(p, v, x, y, has, vl, xl, yl);
+        } else {
+          acc = longitudinal_law(p, v, x, y, (double)A.last_accel[base + m], has, vl, xl, yl, al);
+          if (p.kind == T2D_CTRL_PURE_PURSUIT) {
+            const int pid = A.path_id ? (int)A.path_id[base + m] : -1;
+            if (pid >= 0 && pid < A.n_paths)
+              steer = pure_pursuit_law(p, A.path_v + A.path_off[pid], A.path_off[pid + 1] - A.path_off[pid], v, x, y,
+                                       (double)A.h[base + m]);
+          }
+        }
+        out[j] = A.steer_first ? make_float2((float)steer, (float)acc) : make_float2((float)acc, (float)steer);
+        ctl[j] = true;
+      }
+      // |a| the physics will apply: single_track_kinematics.py:192 clips to the accel range; point_mass.py takes (ax, ay) as is
+      if (tp.model <= T2D_MODEL_DYNAMICS || tp.model == T2D_MODEL_DRIFT)
+        mag[j] = fabsf(clampf(A.steer_first ? out[j].y : out[j].x, tp.accel_lo, tp.accel_hi));
+      else if (tp.model <= T2D_MODEL_POINTMASS_EULER)
+        mag[j] = (float)hypot((double)out[j].x, (double)out[j].y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = lane + 32 * j;
+      if (m >= A.M) continue;
+      if (ctl[j]) reinterpret_cast<float2*>(A.action)[base + m] = out[j];
+      A.last_accel[base + m] = mag[j];
+    }
+  }
+}
+
 }  // namespace t2d
 
 // =============================================================================================
@@ -1069,7 +1230,9 @@ struct t2d_ctx {
   t2d_config cfg{};
   int n_types = 0;
   bool has_pointmass = false;
+  bool has_drift = false;
   bool kin_only = false;
+  float *wheel_f = nullptr, *wheel_r = nullptr;
   Params* d_table = nullptr;
   unsigned char* d_map = nullptr;
   uint8_t* d_fine = nullptr;
@@ -1094,6 +1257,16 @@ struct t2d_ctx {
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
   int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // NPC controllers (t2d_set_controllers / t2d_set_paths / t2d_control)
+  t2d_controller_params* d_ctab = nullptr;
+  int n_ctrl = 0;
+  const uint8_t* ctrl_id = nullptr;
+  const int16_t* ctrl_lead = nullptr;
+  const int16_t* ctrl_path = nullptr;
+  float* ctrl_last_accel = nullptr;
+  PathVertex* d_path_v = nullptr;
+  int* d_path_off = nullptr;
+  int n_paths = 0;
   // t2d_step_host: device staging for the host-resident action / status / done, the copy stream and its events
   static constexpr int MAX_HOST_CHUNKS = 8;
   float* hs_action = nullptr;          // [N][M][2]
@@ -1160,6 +1333,9 @@ int t2d_destroy(t2d_ctx* c) {
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_map) cudaFree(c->d_map);
   if (c->d_fine) cudaFree(c->d_fine);
+  if (c->d_ctab) cudaFree(c->d_ctab);
+  if (c->d_path_v) cudaFree(c->d_path_v);
+  if (c->d_path_off) cudaFree(c->d_path_off);
   if (c->hs_action) cudaFree(c->hs_action);
   if (c->hs_out) cudaFree(c->hs_out);
   if (c->hs_out_pinned) cudaFreeHost(c->hs_out_pinned);
@@ -1182,18 +1358,23 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   if (!c || !table) return fail(T2D_E_INVALID, "ctx/table is NULL");
   if (n_types <= 0 || n_types > T2D_MAX_TYPES) return fail(T2D_E_INVALID, "n_types must be in 1..64");
   static_assert(sizeof(t2d_type_params) == sizeof(AbiParams), "type table layout");
-  static_assert(sizeof(Params) == 96, "device type row");
+  static_assert(sizeof(Params) == 112, "device type row");
   c->has_pointmass = false;
+  bool has_drift = false;
   float rb_max = 0.0f;
   for (int i = 0; i < n_types; ++i) {
     const t2d_type_params& p = table[i];
     if (p.shape == T2D_SHAPE_OBB) rb_max = std::max(rb_max, sqrtf(p.half_len * p.half_len + p.half_wid * p.half_wid) * 1.000002f);
     if (p.shape == T2D_SHAPE_CIRCLE) rb_max = std::max(rb_max, p.radius);
-    if (p.model < 0 || p.model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "type table: unknown model id");
+    if (p.model < 0 || p.model > T2D_MODEL_DRIFT) return fail(T2D_E_INVALID, "type table: unknown model id");
     if (p.shape < 0 || p.shape > T2D_SHAPE_NONE) return fail(T2D_E_INVALID, "type table: unknown shape id");
-    if (p.model <= T2D_MODEL_DYNAMICS && !(p.lf + p.lr > 0.0f)) return fail(T2D_E_INVALID, "type table: lf + lr must be > 0");
+    const bool bicycle = p.model <= T2D_MODEL_DYNAMICS || p.model == T2D_MODEL_DRIFT;
+    if (bicycle && !(p.lf + p.lr > 0.0f)) return fail(T2D_E_INVALID, "type table: lf + lr must be > 0");
     if (p.model == T2D_MODEL_DYNAMICS && !(p.lf > 0.0f && p.I_z > 0.0f))
       return fail(T2D_E_INVALID, "type table: dynamics needs lf > 0 and I_z > 0");
+    if (p.model == T2D_MODEL_DRIFT && !(p.lf > 0.0f && p.I_z > 0.0f && p.mass > 0.0f && p.wheel_radius > 0.0f && p.I_yw > 0.0f))
+      return fail(T2D_E_INVALID, "type table: drift needs lf, I_z, mass, wheel_radius and I_yw > 0");
+    if (p.model == T2D_MODEL_DRIFT) has_drift = true;
     if (p.shape == T2D_SHAPE_OBB && !(p.half_len >= 0.0f && p.half_wid >= 0.0f))
       return fail(T2D_E_INVALID, "type table: negative OBB half extent");
     if (p.shape == T2D_SHAPE_CIRCLE && !(p.radius >= 0.0f)) return fail(T2D_E_INVALID, "type table: negative radius");
@@ -1211,6 +1392,7 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
     CUDA_TRY(cudaMemcpy(c->d_table, rows.data(), n_types * sizeof(Params), cudaMemcpyHostToDevice));
   }
   c->n_types = n_types;
+  c->has_drift = has_drift;
   c->rb_max = rb_max;
   c->kin_only = true;
   for (int i = 0; i < n_types; ++i)
@@ -1360,6 +1542,13 @@ int t2d_bind_state(t2d_ctx* c, float* x, float* y, float* heading, float* speed,
   return T2D_OK;
 }
 
+int t2d_bind_wheel_state(t2d_ctx* c, float* omega_front, float* omega_rear) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if ((omega_front == nullptr) != (omega_rear == nullptr)) return fail(T2D_E_INVALID, "t2d_bind_wheel_state: one array is NULL");
+  c->wheel_f = omega_front; c->wheel_r = omega_rear;
+  return T2D_OK;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Launches K1 over the scenarios [first, first + count) of the bound state; the per-participant / per-scenario
@@ -1370,6 +1559,8 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
   if (!c->d_table || c->n_types == 0) return fail(T2D_E_STATE, "type table not set: call t2d_set_type_table first");
   if (do_physics && !action) return fail(T2D_E_INVALID, "action is NULL");
+  if (do_physics && c->has_drift && !(c->wheel_f && c->wheel_r))
+    return fail(T2D_E_STATE, "the type table holds a SingleTrackDrift row: call t2d_bind_wheel_state first");
   CUDA_TRY(cudaSetDevice(c->device));
   if (count < 0) count = c->N - first;
   if (first < 0 || count <= 0 || first + count > c->N) return fail(T2D_E_INVALID, "scenario range out of bounds");
@@ -1377,6 +1568,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   StepArgs A{};
   A.x = c->x + p0; A.y = c->y + p0; A.h = c->h + p0; A.v = c->v + p0; A.vx = c->vx + p0; A.vy = c->vy + p0;
   A.type_id = c->type_id + p0; A.step_count = c->step_count + first;
+  A.wheel_f = c->wheel_f ? c->wheel_f + p0 : nullptr; A.wheel_r = c->wheel_r ? c->wheel_r + p0 : nullptr;
   A.action = action; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
   A.scn_status = scn_status; A.done = done;
   A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine; A.mh = c->mh;
@@ -1591,16 +1783,102 @@ int t2d_lidar_scan(t2d_ctx* c, int n_beams, float max_range, const double* beam_
   return T2D_OK;
 }
 
+int t2d_set_controllers(t2d_ctx* c, const t2d_controller_params* table, int n_rows, const uint8_t* ctrl_id,
+                        const int16_t* lead_index, const int16_t* path_id, float* last_accel) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!table) {
+    if (c->d_ctab) cudaFree(c->d_ctab);
+    c->d_ctab = nullptr; c->n_ctrl = 0; c->ctrl_id = nullptr; c->ctrl_lead = nullptr; c->ctrl_path = nullptr;
+    c->ctrl_last_accel = nullptr;
+    return T2D_OK;
+  }
+  if (n_rows <= 0 || n_rows > T2D_MAX_CONTROLLERS) return fail(T2D_E_INVALID, "n_rows must be in 1..T2D_MAX_CONTROLLERS");
+  if (!ctrl_id || !last_accel) return fail(T2D_E_INVALID, "t2d_set_controllers: ctrl_id / last_accel is NULL");
+  for (int i = 0; i < n_rows; ++i) {
+    const t2d_controller_params& p = table[i];
+    if (p.kind < T2D_CTRL_EXTERNAL || p.kind > T2D_CTRL_PURE_PURSUIT) return fail(T2D_E_INVALID, "unknown controller kind");
+    if (p.kind == T2D_CTRL_PURE_PURSUIT && !(p.min_pre_aiming_distance > 0.0f))
+      return fail(T2D_E_INVALID, "min_pre_aiming_distance must be positive");   // pure_pursuit_controller.py:30-31
+    if (p.kind >= T2D_CTRL_CRUISE && p.target_speed < 0.0f)
+      return fail(T2D_E_INVALID, "target_speed must be non-negative");          // acceleration_controller.py:48-49
+  }
+  if (c->d_ctab) { cudaFree(c->d_ctab); c->d_ctab = nullptr; }
+  CUDA_TRY(cudaMalloc(&c->d_ctab, sizeof(t2d_controller_params) * n_rows));
+  CUDA_TRY(cudaMemcpy(c->d_ctab, table, sizeof(t2d_controller_params) * n_rows, cudaMemcpyHostToDevice));
+  c->n_ctrl = n_rows; c->ctrl_id = ctrl_id; c->ctrl_lead = lead_index; c->ctrl_path = path_id; c->ctrl_last_accel = last_accel;
+  return T2D_OK;
+}
+
+int t2d_set_paths(t2d_ctx* c, const float* xy, const int32_t* offsets, int n_paths) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->d_path_v) { cudaFree(c->d_path_v); c->d_path_v = nullptr; }
+  if (c->d_path_off) { cudaFree(c->d_path_off); c->d_path_off = nullptr; }
+  c->n_paths = 0;
+  if (n_paths == 0 || !xy) return T2D_OK;
+  if (n_paths < 0 || !offsets) return fail(T2D_E_INVALID, "t2d_set_paths: bad argument");
+  if (offsets[0] != 0) return fail(T2D_E_INVALID, "offsets[0] must be 0");
+  for (int p = 0; p < n_paths; ++p)
+    if (offsets[p + 1] - offsets[p] < 2) return fail(T2D_E_INVALID, "a path needs at least 2 vertices");
+  const int V = offsets[n_paths];
+  std::vector<PathVertex> pv((size_t)V);
+  for (int p = 0; p < n_paths; ++p) {
+    double acc = 0.0;   // the running arc length of LineString.interpolate's walk, in float64
+    for (int i = offsets[p]; i < offsets[p + 1]; ++i) {
+      pv[i].x = xy[2 * i]; pv[i].y = xy[2 * i + 1];
+      pv[i].cum = acc;
+      pv[i].len = 0.0;
+      if (i + 1 < offsets[p + 1]) {
+        pv[i].len = hypot((double)xy[2 * i + 2] - (double)xy[2 * i], (double)xy[2 * i + 3] - (double)xy[2 * i + 1]);
+        acc += pv[i].len;
+      }
+    }
+  }
+  CUDA_TRY(cudaMalloc(&c->d_path_v, sizeof(PathVertex) * (size_t)V));
+  CUDA_TRY(cudaMemcpy(c->d_path_v, pv.data(), sizeof(PathVertex) * (size_t)V, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&c->d_path_off, sizeof(int) * (size_t)(n_paths + 1)));
+  CUDA_TRY(cudaMemcpy(c->d_path_off, offsets, sizeof(int) * (size_t)(n_paths + 1), cudaMemcpyHostToDevice));
+  c->n_paths = n_paths;
+  return T2D_OK;
+}
+
+int t2d_control(t2d_ctx* c, float* action, void* stream) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
+  if (!c->d_table || c->n_types == 0) return fail(T2D_E_STATE, "type table not set: call t2d_set_type_table first");
+  if (!c->d_ctab) return fail(T2D_E_STATE, "controllers not set: call t2d_set_controllers first");
+  if (!action) return fail(T2D_E_INVALID, "action is NULL");
+  if (reinterpret_cast<uintptr_t>(action) % 8 != 0) return fail(T2D_E_INVALID, "action must be 8-byte aligned");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CtrlArgs A{};
+  A.x = c->x; A.y = c->y; A.h = c->h; A.v = c->v; A.type_id = c->type_id; A.table = c->d_table; A.n_types = c->n_types;
+  A.ctab = c->d_ctab; A.n_ctrl = c->n_ctrl; A.ctrl_id = c->ctrl_id; A.lead = c->ctrl_lead; A.path_id = c->ctrl_path;
+  A.path_v = c->d_path_v; A.path_off = c->d_path_off; A.n_paths = c->n_paths;
+  A.last_accel = c->ctrl_last_accel; A.action = action;
+  A.N = c->N; A.M = c->M; A.steer_first = (c->cfg.flags & T2D_CFG_STEER_FIRST) ? 1 : 0;
+  const int warps_per_cta = 4;
+  const int grid = std::max(1, std::min((c->N + warps_per_cta - 1) / warps_per_cta, c->sm_count * 16));
+  t2d_control_kernel<<<grid, warps_per_cta * 32, 0, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
 int t2d_physics_step(int device, const t2d_type_params* params, int interval_ms, int delta_t_ms, int n, float* x, float* y,
-                     float* heading, float* speed, float* vx, float* vy, const float* action, float* applied, void* stream) {
+                     float* heading, float* speed, float* vx, float* vy, float* omega_front, float* omega_rear,
+                     const float* action, float* applied, void* stream) {
   if (!params) return fail(T2D_E_INVALID, "params is NULL");
   if (n < 0) return fail(T2D_E_INVALID, "n must be >= 0");
   if (n == 0) return T2D_OK;
   if (!x || !y || !heading || !speed || !vx || !vy || !action) return fail(T2D_E_INVALID, "t2d_physics_step: NULL array");
   if (interval_ms <= 0 || delta_t_ms <= 0) return fail(T2D_E_INVALID, "interval_ms and delta_t_ms must be > 0");
-  if (params->model < 0 || params->model > T2D_MODEL_STATIC) return fail(T2D_E_INVALID, "unknown model id");
+  if (params->model < 0 || params->model > T2D_MODEL_DRIFT) return fail(T2D_E_INVALID, "unknown model id");
+  if (params->model == T2D_MODEL_DRIFT && !(omega_front && omega_rear))
+    return fail(T2D_E_INVALID, "t2d_physics_step: SingleTrackDrift needs the wheel-speed arrays");
   CUDA_TRY(cudaSetDevice(device));
   PhysArgs A{};
+  A.wheel_f = omega_front; A.wheel_r = omega_rear;
   {
     AbiParams a;
     memcpy(&a, params, sizeof(AbiParams));

@@ -42,6 +42,7 @@ constexpr int MODEL_DYNAMICS = 1;
 constexpr int MODEL_POINTMASS_NEWTON = 2;
 constexpr int MODEL_POINTMASS_EULER = 3;
 constexpr int MODEL_STATIC = 4;
+constexpr int MODEL_DRIFT = 5;
 constexpr int SHAPE_OBB = 0;
 constexpr int SHAPE_CIRCLE = 1;
 constexpr int SHAPE_NONE = 2;
@@ -52,15 +53,16 @@ constexpr float INV_TWO_PI = 0.15915494309189535f;
 constexpr double TWO_PI_D = 6.283185307179586476925286766559;
 constexpr double G_ACC = 9.81;                     // physics_model_base.py:25
 
-// Mirror of t2d_type_params (include/t2d_b200.h); 19 words.
+// Mirror of t2d_type_params (include/t2d_b200.h); 23 words.
 struct AbiParams {
   float half_len, half_wid, radius, lf, lr;
   float steer_lo, steer_hi, speed_lo, speed_hi, accel_lo, accel_hi;
   float mass, mass_height, mu, I_z, cf, cr;
   int32_t model, shape;
+  float wheel_radius, T_sb, T_se, I_yw;   // SingleTrackDrift only
 };
 
-// The row the kernels read: the ABI row plus constants derived once on the host (24 words = 96 B).
+// The row the kernels read: the ABI row plus constants derived once on the host (28 words = 112 B).
 struct Params : AbiParams {
   float inv_L;        // 1 / (lf + lr)
   float lr_over_L;    // lr / (lf + lr)
@@ -306,6 +308,7 @@ struct OneIO {
   float x, y, h, v, vx, vy;  // state in / out
   float ch, sh;              // out: (cos, sin)(new heading)
   float a0, a1;              // in: raw action; out: applied action
+  float w0, w1;              // SingleTrackDrift only: front / rear wheel angular speed in / out
 };
 
 T2D_HD void dynamics_step(OneIO& io, const Params& p, int n_steps, double dt) {
@@ -357,6 +360,131 @@ T2D_HD void dynamics_step(OneIO& io, const Params& p, int n_steps, double dt) {
   io.x = (float)x; io.y = (float)y; io.h = hn; io.v = (float)v;
   io.vx = io.v * ch; io.vy = io.v * sh;      // State.velocity of a State without vx, vy (state.py:160-165)
   io.ch = ch; io.sh = sh;
+}
+
+// ------------------------------------------------------------------------------------------
+// SingleTrackDrift.step/_step  (single_track_drift.py:467-499,340-465) with the built-in tyre
+// (class Tire, :14-49; the reference evaluates every force at camber gamma = 0), fp64.
+// This model DOES take the remainder sub-step (:352-355).  Wheel speeds travel in io.w0 / io.w1.
+// ------------------------------------------------------------------------------------------
+namespace tire {
+constexpr double p_cx1 = 1.6411, p_dx1 = 1.1739, p_ex1 = 0.4640, p_kx1 = 22.303, p_hx1 = 1.2297e-3, p_vx1 = -8.8098e-6;
+constexpr double r_bx1 = 13.276, r_bx2 = -13.778, r_ex1 = 1.2568, r_cx1 = 0.6522, r_hx1 = 5.0722e-3;
+constexpr double p_cy1 = 1.3507, p_dy1 = 1.0489, p_ey1 = -7.4722e-3, p_ky1 = -21.920;
+constexpr double r_by1 = 7.1433, r_by2 = 9.1917, r_by3 = -2.7856e-2, r_cy1 = 1.0719, r_ey1 = -0.2757, r_hy1 = 5.7448e-6;
+constexpr double r_vy1 = -2.7825e-2, r_vy4 = 12.120, r_vy5 = 1.9, r_vy6 = -10.704;
+}  // namespace tire
+
+T2D_HD double safe_div(double u) { return fabs(u) > 1e-6 ? u : (u >= 0.0 ? 1e-6 : -1e-6); }   // :287,289,308-309,345
+T2D_HD double magic(double B, double C, double E, double arg) {                                 // C atan(B a - E (B a - atan(B a)))
+  const double ba = B * arg;
+  return C * atan(ba - E * (ba - atan(ba)));
+}
+
+struct TireForces { double F_xf, F_xr, F_yf, F_yr; };
+
+// _tire_forces :282-338 and the four Pacejka helpers :185-280 (gamma = 0: S_hy = S_vy = 0, mu_y = p_dy1, mu_x = p_dx1)
+T2D_HD TireForces drift_tire_forces(double v_safe, double delta, double d_phi, double beta, double om_f, double om_r, double lf,
+                                    double lr, double mass, double radius) {
+  using namespace tire;
+  double sb, cb, sd, cd;
+  sincos(beta, &sb, &cb);
+  sincos(delta, &sd, &cd);
+  const double vs = safe_div(v_safe);                                                        // :287
+  const double cbs = safe_div(cb);                                                           // :288-289
+  const double alpha_f = atan((vs * sb + d_phi * lf) / (vs * cbs)) - delta;                  // :292-294
+  const double alpha_r = atan((vs * sb - d_phi * lr) / (vs * cbs));                          // :295
+  const double L = lf + lr;
+  const double F_zf = (mass * G_ACC * lr) / L, F_zr = (mass * G_ACC * lf) / L;               // :298-299
+  const double u_wf = vs * cbs * cd + (vs * sb + lf * d_phi) * sd;                           // :302-304
+  const double u_wr = vs * cbs;                                                              // :305
+  const double s_f = 1.0 - radius * om_f / safe_div(u_wf);                                   // :308-313
+  const double s_r = 1.0 - radius * om_r / safe_div(u_wr);
+  TireForces out;
+  for (int axle = 0; axle < 2; ++axle) {
+    const double kappa = axle ? s_r : s_f, alpha = axle ? alpha_r : alpha_f, F_z = axle ? F_zr : F_zf;
+    // pure slip, longitudinal :185-203
+    const double D_x = p_dx1 * F_z;
+    const double B_x = (p_kx1 * F_z) / (p_cx1 * D_x + 1e-6);
+    const double F0_x = D_x * sin(magic(B_x, p_cx1, p_ex1, -kappa + p_hx1) + p_vx1 * F_z);
+    // pure slip, lateral :205-224
+    const double D_y = p_dy1 * F_z;
+    const double B_y = (p_ky1 * F_z) / (p_cy1 * D_y + 1e-6);
+    const double F0_y = D_y * sin(magic(B_y, p_cy1, p_ey1, alpha));
+    // combined slip, longitudinal :226-250
+    const double B_xa = r_bx1 * cos(atan(r_bx2 * kappa));
+    const double D_xa = F0_x / cos(magic(B_xa, r_cx1, r_ex1, r_hx1));
+    const double F_x = D_xa * cos(magic(B_xa, r_cx1, r_ex1, alpha + r_hx1));
+    // combined slip, lateral :252-280
+    const double B_yk = r_by1 * cos(atan(r_by2 * (alpha - r_by3)));
+    const double D_yk = F0_y / cos(magic(B_yk, r_cy1, r_ey1, r_hy1));
+    const double D_vyk = p_dy1 * F_z * r_vy1 * cos(atan(r_vy4 * alpha));
+    const double S_vyk = D_vyk * sin(r_vy5 * atan(r_vy6 * kappa));
+    const double F_y = D_yk * cos(magic(B_yk, r_cy1, r_ey1, kappa + r_hy1)) + S_vyk;
+    if (axle) { out.F_xr = F_x; out.F_yr = F_y; } else { out.F_xf = F_x; out.F_yf = F_y; }
+  }
+  return out;
+}
+
+T2D_HD void drift_step(OneIO& io, const Params& p, int n_steps, double dt_main, double dt_rem) {
+  const double lf = p.lf, lr = p.lr, L = (double)p.lf + (double)p.lr;
+  const double accel = clampd(io.a0, p.accel_lo, p.accel_hi);    // :490
+  const double delta = clampd(io.a1, p.steer_lo, p.steer_hi);    // :491
+  io.a0 = (float)accel;
+  io.a1 = (float)delta;
+  const double mass = p.mass, radius = p.wheel_radius, T_sb = p.T_sb, T_se = p.T_se, Iz = p.I_z, Iyw = p.I_yw;
+  const double tan_d = tan(delta), cos_d = cos(delta), sin_d = sin(delta);
+  double x = io.x, y = io.y, phi = io.h, v = io.v, om_f = io.w0, om_r = io.w1;
+  double d_phi = v / L * tan_d;                                   // :360
+  double beta = atan(lr / lf * tan_d);                            // :361
+  const double T_B = accel > 0.0 ? 0.0 : mass * radius * accel;   // :363-368
+  const double T_E = accel > 0.0 ? mass * radius * accel : 0.0;
+  const double vlo = p.speed_lo, vhi = p.speed_hi;
+  const int total = n_steps + (dt_rem > 0.0 ? 1 : 0);
+  for (int it = 0; it < total; ++it) {                            // :370-455
+    const double dt = it < n_steps ? dt_main : dt_rem;
+    const double v_safe = safe_div(v);
+    const TireForces F = drift_tire_forces(v_safe, delta, d_phi, beta, om_f, om_r, lf, lr, mass, radius);
+    double sn, cs, sb, cb;
+    sincos(phi + beta, &sn, &cs);
+    sincos(beta, &sb, &cb);
+    const double dx = v * cs, dy = v * sn;
+    double dv, d_beta, d_om_f, d_om_r;
+    if (fabs(v) >= 0.1) {                                         // :381
+      double sdb, cdb;
+      sincos(delta - beta, &sdb, &cdb);
+      dv = 1.0 / mass * (-F.F_yf * sdb + F.F_yr * sb + F.F_xr * cb + F.F_xf * cdb);                    // :382-391
+      d_beta = -d_phi + 1.0 / (mass * v_safe) * (F.F_yf * cdb + F.F_yr * cb - F.F_xr * sb + F.F_xf * sdb);   // :392-397
+      const double dd_phi = 1.0 / Iz * (F.F_yf * cos_d * lf - F.F_yr * lr + F.F_xf * sin_d * lf);      // :398-406
+      d_phi += dd_phi * dt;                                                                            // :407
+      d_om_f = 1.0 / Iyw * (-radius * F.F_xf + T_sb * T_B + T_se * T_E);                               // :408-410
+      d_om_r = 1.0 / Iyw * (-radius * F.F_xr + (1.0 - T_sb) * T_B + (1.0 - T_se) * T_E);               // :411-415
+    } else {
+      dv = accel;                                                                                      // :417
+      d_beta = lr / ((1.0 + tan_d * lr / L) * (1.0 + tan_d * lr / L)) / L / (cos_d * cos_d) * delta;   // :418-424
+      d_phi += v * cb / L * tan_d * dt;                                                                // :434
+      d_om_f = 1.0 / (cos_d * radius) * (accel * cb - v * sb * d_beta + v * cb * tan_d * delta);       // :435-443
+      d_om_r = 1.0 / radius * (accel * cb - v * sb * d_beta);                                          // :444
+    }
+    x += dx * dt;                                                 // :446-453
+    y += dy * dt;
+    v += dv * dt;
+    phi += d_phi * dt;
+    beta += d_beta * dt;
+    om_f += d_om_f * dt;
+    om_r += d_om_r * dt;
+    v = clampd(v, vlo, vhi);                                      // :455
+  }
+  double hd = fmod(phi, TWO_PI_D);                               // np.mod(phi, 2 pi) :461
+  if (hd < 0.0) hd += TWO_PI_D;
+  float hn = (float)hd;
+  if (hn >= TWO_PI_HI) hn = 0.0f;
+  float sh, ch;
+  sincos_fast(hn, &sh, &ch);
+  io.x = (float)x; io.y = (float)y; io.h = hn; io.v = (float)v;
+  io.vx = io.v * ch; io.vy = io.v * sh;      // State.velocity of a State without vx, vy (state.py:160-165)
+  io.ch = ch; io.sh = sh;
+  io.w0 = (float)om_f; io.w1 = (float)om_r;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ class PhysicsModelBase(ABC):
             d = min(d, interval)
         return d
 
-    def _launch(self, params, interval, n, x, y, heading, speed, vx, vy, action, applied):
+    def _launch(self, params, interval, n, x, y, heading, speed, vx, vy, action, applied, omega_f=None, omega_r=None):
         """One call of the C ABI's ``t2d_physics_step`` on the tensors' device and current stream."""
         import torch
 
@@ -57,7 +57,8 @@ class PhysicsModelBase(ABC):
         dev = x.device
         if dev.type != "cuda":
             raise RuntimeError("tactics2d_b200 physics runs on a CUDA device only (there is no CPU implementation)")
-        for t in (x, y, heading, speed, vx, vy, action) + ((applied,) if applied is not None else ()):
+        extra = tuple(t for t in (applied, omega_f, omega_r) if t is not None)
+        for t in (x, y, heading, speed, vx, vy, action) + extra:
             if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("state/action tensors must be contiguous fp32 tensors on one CUDA device")
         c = params.to_c()
@@ -65,4 +66,4 @@ class PhysicsModelBase(ABC):
         p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
         _lib.check(lib.t2d_physics_step(dev.index if dev.index is not None else torch.cuda.current_device(), C.byref(c),
                                         int(interval), int(self.delta_t), int(n), p(x), p(y), p(heading), p(speed),
-                                        p(vx), p(vy), p(action), p(applied), stream))
+                                        p(vx), p(vy), p(omega_f), p(omega_r), p(action), p(applied), stream))

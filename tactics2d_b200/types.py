@@ -17,7 +17,7 @@ import numpy as np
 
 from ._lib import TypeParamsC
 
-MODEL_KINEMATICS, MODEL_DYNAMICS, MODEL_POINTMASS_NEWTON, MODEL_POINTMASS_EULER, MODEL_STATIC = range(5)
+MODEL_KINEMATICS, MODEL_DYNAMICS, MODEL_POINTMASS_NEWTON, MODEL_POINTMASS_EULER, MODEL_STATIC, MODEL_DRIFT = range(6)
 SHAPE_OBB, SHAPE_CIRCLE, SHAPE_NONE = range(3)
 TYPE_INACTIVE = 255
 MAX_TYPES = 64
@@ -67,6 +67,10 @@ class TypeParams:
     cr: float = 20.89
     model: int = MODEL_KINEMATICS
     shape: int = SHAPE_OBB
+    wheel_radius: float = 0.344     # SingleTrackDrift defaults, single_track_drift.py:98-107
+    T_sb: float = 0.76
+    T_se: float = 1.0
+    I_yw: float = 1.7
     name: str = ""
 
     def to_c(self) -> TypeParamsC:
@@ -81,8 +85,8 @@ class TypeParams:
         """``Vehicle`` + ``load_from_template`` (vehicle.py:107-142,179-221): steer +-round(pi/6, 3),
         speed (-16.67, max_speed), accel (-max_decel, max_accel = round(27.78/t_0_100, 3));
         physics as ``_auto_construct_physics_model`` (:148-157): lf = L/2 - front_overhang,
-        lr = L/2 - rear_overhang.  ``model="dynamics"`` uses kerb_weight and height/2
-        (single_track_dynamics.py:79-80 docstring)."""
+        lr = L/2 - rear_overhang.  ``model="dynamics"`` / ``"drift"`` use kerb_weight and height/2
+        (single_track_dynamics.py:79-80 docstring); drift keeps the wheel defaults of single_track_drift.py:98-107."""
         from .participant.element.participant_template import VEHICLE_TEMPLATE
 
         t = dict(VEHICLE_TEMPLATE[type_name])
@@ -94,7 +98,7 @@ class TypeParams:
                    steer_lo=-max_steer, steer_hi=max_steer, speed_lo=-16.67, speed_hi=t["max_speed"],
                    accel_lo=-t["max_decel"], accel_hi=max_accel, mass=t["kerb_weight"],
                    mass_height=t["height"] / 2,
-                   model=MODEL_DYNAMICS if model == "dynamics" else MODEL_KINEMATICS,
+                   model={"dynamics": MODEL_DYNAMICS, "drift": MODEL_DRIFT}.get(model, MODEL_KINEMATICS),
                    shape=SHAPE_OBB, name=type_name)
 
     @classmethod

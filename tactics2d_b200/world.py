@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .types import TYPE_INACTIVE, TypeTable
+from .types import MODEL_DRIFT, TYPE_INACTIVE, TypeTable
 
 CFG_ANY_PARTICIPANT = 1
 CFG_STEER_FIRST = 2
@@ -84,6 +84,12 @@ class BatchedWorld:
             status=torch.ones(self.N, dtype=torch.uint8, device=self.device),
             done=torch.zeros(self.N, dtype=torch.uint8, device=self.device))
         self._bind()
+        # SingleTrackDrift participants carry their wheel speeds (single_track_drift.py:467-499)
+        self.omega_front = self.omega_rear = None
+        if any(r.model == MODEL_DRIFT for r in type_table.rows):
+            self.omega_front = torch.zeros(shape, **f)
+            self.omega_rear = torch.zeros(shape, **f)
+            _lib.check(self.lib.t2d_bind_wheel_state(self._ctx, _ptr(self.omega_front), _ptr(self.omega_rear)))
         self.segments = None
         self.bounds = None
         self._goal = None
@@ -154,7 +160,72 @@ class BatchedWorld:
         _lib.check(self.lib.t2d_set_goal(self._ctx, _ptr(g["target"]), float(arrival_threshold), int(no_action_max_step),
                                          _ptr(g["iou"]), _ptr(g["last_pose"]), _ptr(g["count"])))
 
+    # ------------------------------------------------------------------ NPC controllers
+    def set_paths(self, paths):
+        """Pure-pursuit waypoint polylines: a list of ``[V_p, 2]`` arrays (the ``waypoints`` of
+        ``PurePursuitController.step``, pure_pursuit_controller.py:76); ``path_id`` of ``set_controllers`` indexes it."""
+        paths = [np.ascontiguousarray(np.asarray(p, dtype=np.float32).reshape(-1, 2)) for p in paths]
+        self.paths = paths
+        if not paths:
+            _lib.check(self.lib.t2d_set_paths(self._ctx, _ptr(None), _ptr(None), 0))
+            return
+        xy = np.ascontiguousarray(np.concatenate(paths, 0))
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p) for p in paths])
+        _lib.check(self.lib.t2d_set_paths(self._ctx, C.c_void_p(xy.ctypes.data), C.c_void_p(off.ctypes.data), len(paths)))
+
+    def set_controllers(self, controllers, ctrl_id, lead_index=None, path_id=None, last_accel=None):
+        """Hand the non-ego agents to on-device controllers.  ``controllers``: list of ``tactics2d_b200.controller``
+        objects (or ``ControllerParamsC`` rows); ``ctrl_id`` [N, M] uint8: the participant's row, 255 for "action comes
+        from the caller"; ``lead_index`` [N, M] int16: its leading vehicle (``leading_state`` / ``front_state``), -1 for
+        none; ``path_id`` [N, M] int16: its pure-pursuit path (``set_paths``), -1 for none; ``last_accel`` [N, M]:
+        ``State.accel`` of the previous tick (default zeros).  ``None`` for ``controllers`` removes them."""
+        if controllers is None:
+            self._ctrl = None
+            _lib.check(self.lib.t2d_set_controllers(self._ctx, _ptr(None), 0, _ptr(None), _ptr(None), _ptr(None), _ptr(None)))
+            return
+        rows = [c if isinstance(c, _lib.ControllerParamsC) else c.params() for c in controllers]
+        arr = (_lib.ControllerParamsC * len(rows))(*rows)
+
+        def dev(a, dtype, fill):
+            if a is None:
+                return None
+            t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+            return t.to(device=self.device, dtype=dtype).reshape(self.N, self.M).contiguous()
+
+        cid = dev(ctrl_id, torch.uint8, 255)
+        lead = dev(lead_index, torch.int16, -1)
+        pid = dev(path_id, torch.int16, -1)
+        la = dev(last_accel, torch.float32, 0.0)
+        if la is None:
+            la = torch.zeros((self.N, self.M), dtype=torch.float32, device=self.device)
+        self._ctrl = dict(rows=arr, ctrl_id=cid, lead_index=lead, path_id=pid, last_accel=la)
+        _lib.check(self.lib.t2d_set_controllers(self._ctx, arr, len(rows), _ptr(cid), _ptr(lead), _ptr(pid), _ptr(la)))
+
+    @property
+    def last_accel(self) -> Optional[torch.Tensor]:
+        c = getattr(self, "_ctrl", None)
+        return None if c is None else c["last_accel"]
+
+    def control(self, action: torch.Tensor) -> torch.Tensor:
+        """Fill the rows of ``action`` [N, M, 2] that belong to controlled participants (IN PLACE; the other rows keep
+        the caller's values) and refresh ``last_accel`` - ``ControllerBase.step`` of every NPC in one launch.  Call it
+        after writing the external (ego) actions and before ``step``."""
+        if action.device != self.device or action.dtype != torch.float32:
+            raise ValueError("action must be an fp32 tensor on the world's device")
+        if tuple(action.shape) != (self.N, self.M, 2) or not action.is_contiguous():
+            raise ValueError(f"action must be contiguous [{self.N}, {self.M}, 2]")
+        _lib.check(self.lib.t2d_control(self._ctx, _ptr(action), self._stream()))
+        return action
+
     # ------------------------------------------------------------------ state
+    def set_wheel_state(self, omega_front, omega_rear):
+        """Wheel angular speeds [N, M] of the SingleTrackDrift participants (``omega_wf`` / ``omega_wr``)."""
+        if self.omega_front is None:
+            raise ValueError("the type table holds no SingleTrackDrift row")
+        for dst, src in ((self.omega_front, omega_front), (self.omega_rear, omega_rear)):
+            dst.copy_(torch.as_tensor(np.asarray(src) if not torch.is_tensor(src) else src).to(dst.dtype).reshape(dst.shape))
+
     def set_state(self, x, y, heading, speed=None, vx=None, vy=None, type_id=None):
         """Copy host or device arrays [N, M] into the SoA state.  Missing ``vx, vy`` are derived as
         ``State.velocity`` does (state.py:160-165); missing ``speed`` as ``State.speed`` (:143-146)."""
@@ -177,7 +248,11 @@ class BatchedWorld:
             put(self.type_id, type_id)
 
     def state_numpy(self) -> dict:
-        return {k: getattr(self, k).detach().cpu().numpy() for k in ("x", "y", "heading", "speed", "vx", "vy")}
+        out = {k: getattr(self, k).detach().cpu().numpy() for k in ("x", "y", "heading", "speed", "vx", "vy")}
+        if self.omega_front is not None:
+            out["omega_wf"] = self.omega_front.detach().cpu().numpy()
+            out["omega_wr"] = self.omega_rear.detach().cpu().numpy()
+        return out
 
     # ------------------------------------------------------------------ the hot path
     def step(self, action: torch.Tensor) -> StepResult:

@@ -99,6 +99,20 @@ void hs_outbound(int n, const float* a, const float* bounds, int32_t* out_f32, i
   }
 }
 
+// SingleTrackDrift: wheel speeds in / out next to the state
+void hs_drift(int n, const AbiParams* ap, int n_steps, double dt, double dt_rem, float* x, float* y, float* h, float* v,
+              float* wf, float* wr, const float* action, float* applied) {
+  const Params p = derive_params(*ap);
+  for (int i = 0; i < n; ++i) {
+    OneIO io;
+    io.x = x[i]; io.y = y[i]; io.h = h[i]; io.v = v[i]; io.vx = 0.0f; io.vy = 0.0f; io.w0 = wf[i]; io.w1 = wr[i];
+    io.a0 = action[2 * i]; io.a1 = action[2 * i + 1]; io.ch = 1.0f; io.sh = 0.0f;
+    drift_step(io, p, n_steps, dt, dt_rem);
+    x[i] = io.x; y[i] = io.y; h[i] = io.h; v[i] = io.v; wf[i] = io.w0; wr[i] = io.w1;
+    applied[2 * i] = io.a0; applied[2 * i + 1] = io.a1;
+  }
+}
+
 float hs_wrap(float phi) { return wrap_two_pi(phi); }
 
 // rows: x, y, heading, l, w (fp32, as the kernel sees them)

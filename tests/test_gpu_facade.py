@@ -341,3 +341,115 @@ def test_lidar_scan_matches_reference_restatement(cuda_device, n_beams, max_rang
     pts = lidar.get_points(w)
     assert pts.shape == (40, n_beams, 2) and torch.isfinite(pts[torch.from_numpy(hit).to(cuda_device)]).all()
     w.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SingleTrackDrift: the fourth physics model
+# ---------------------------------------------------------------------------------------------------------------
+def _drift_oracle(g, s6, act, name, interval, delta_t):
+    from oracle import physics as P
+
+    f32 = lambda v: np.float64(np.float32(v))
+    inf = (-np.inf, np.inf)
+    rng = {k: (tuple(np.float32(g[k]).astype(np.float64)) if name == "con" else inf) for k in ("steer_range", "speed_range", "accel_range")}
+    r = P.step_drift(s6[:, 0], s6[:, 1], s6[:, 2], s6[:, 3], s6[:, 4], s6[:, 5], act[:, 0], act[:, 1], f32(g["lf"]), f32(g["lr"]),
+                     f32(g["mass"]), f32(0.344), f32(0.76), 1.0, 1500.0, f32(1.7), rng["steer_range"], rng["speed_range"],
+                     rng["accel_range"], interval, delta_t)
+    return np.stack([r[f] for f in ("x", "y", "heading", "speed", "omega_wf", "omega_wr", "accel", "delta")], 1)
+
+
+@pytest.mark.parametrize("name", ["con", "unc"])
+@pytest.mark.parametrize("interval,delta_t", [(100, 5), (9, 5), (50, 3)])
+def test_drift_step_batch_vs_reference(cuda_device, name, interval, delta_t):
+    """SingleTrackDrift.step_batch: the reference's own outputs on the rows where rounding the parameters to fp32 is
+    harmless, the float64 restatement with the fp32 parameters on every row (the model is stiff at 5 ms; see
+    tests/test_hostsim_math.py::test_drift_vs_reference_golden)."""
+    import torch
+
+    from tactics2d_b200.physics import SingleTrackDrift
+    from tests.util import heading_err, rel_err
+
+    g = np.load(os.path.join(GOLD, "physics_drift.npz"))
+    kw = {} if name == "unc" else {k: tuple(float(v) for v in g[k]) for k in ("steer_range", "speed_range", "accel_range")}
+    model = SingleTrackDrift(lf=float(g["lf"]), lr=float(g["lr"]), mass=float(g["mass"]), mass_height=float(g["mass_height"]),
+                             interval=interval, delta_t=delta_t, **kw)
+    s0 = np.concatenate([g["states"], g["omega"]], 1)
+    t = [torch.tensor(s0[:, i], dtype=torch.float32, device=cuda_device) for i in range(6)]
+    a = torch.tensor(g["actions"], dtype=torch.float32, device=cuda_device)
+    _, _, ac, dc = model.step_batch(*t, a[:, 0].contiguous(), a[:, 1].contiguous(), interval)
+    got = np.stack([u.cpu().numpy().astype(np.float64) for u in t] + [ac.cpu().numpy().astype(np.float64), dc.cpu().numpy().astype(np.float64)], 1)
+    ref64 = g[f"drift_{name}_{interval}_{delta_t}"][:, 0]
+    ref32 = _drift_oracle(g, s0, g["actions"], name, interval, delta_t)
+
+    def check(got, ref):
+        for c in (0, 1, 3, 4, 5, 6, 7):
+            assert rel_err(got[:, c], ref[:, c]).max() < 1e-5, c
+        assert heading_err(got[:, 2], ref[:, 2]).max() < 1e-5
+
+    calm = (np.abs(ref64 - ref32) / np.maximum(1.0, np.abs(ref64))).max(1) < 2e-7
+    assert calm.sum() >= 20
+    check(got[calm], ref64[calm])
+    check(got, ref32)
+
+
+def test_drift_single_state_api(cuda_device):
+    from tactics2d_b200.participant.trajectory import State
+    from tactics2d_b200.physics import SingleTrackDrift
+
+    g = np.load(os.path.join(GOLD, "physics_drift.npz"))
+    kw = {k: tuple(float(v) for v in g[k]) for k in ("steer_range", "speed_range", "accel_range")}
+    model = SingleTrackDrift(lf=float(g["lf"]), lr=float(g["lr"]), mass=float(g["mass"]), mass_height=float(g["mass_height"]), **kw)
+    s0 = np.concatenate([g["states"], g["omega"]], 1)
+    ref64 = g["drift_con_100_5"][:, 0]
+    ref32 = _drift_oracle(g, s0, g["actions"], "con", 100, 5)
+    calm = np.nonzero((np.abs(ref64 - ref32) / np.maximum(1.0, np.abs(ref64))).max(1) < 2e-7)[0]
+    for i in calm[:4]:
+        st = State(0, x=s0[i, 0], y=s0[i, 1], heading=s0[i, 2], speed=s0[i, 3])
+        nxt, wf, wr, a, d = model.step(st, s0[i, 4], s0[i, 5], g["actions"][i, 0], g["actions"][i, 1])
+        assert nxt.frame == 100 and nxt.vx is None and nxt.vy is None
+        got = np.array([nxt.x, nxt.y, nxt.heading, nxt.speed, wf, wr, a, d])
+        assert np.all(np.abs(got - ref64[i]) <= 1e-5 * np.maximum(1.0, np.abs(ref64[i])))
+    with pytest.raises(NotImplementedError):
+        SingleTrackDrift(lf=1.0, lr=1.0, mass=1000.0, mass_height=0.5, tire=object())
+
+
+def test_drift_participants_inside_the_world_tick(cuda_device):
+    """Drift vehicles next to kinematic ones in t2d_step: state and wheel speeds teacher-forced against the restatement,
+    events bit-exact on the poses the GPU wrote."""
+    import torch
+
+    from oracle import scenario as O
+    from tactics2d_b200 import BatchedWorld, TypeParams, TypeTable, synthetic
+    from tests.util import assert_state_close, rel_err
+
+    n, m = 24, 16
+    scene = synthetic.config2(n, m, seed=31)
+    rows = [TypeParams.vehicle("medium_car"), TypeParams.vehicle("medium_car", model="drift"),
+            TypeParams.vehicle("large_car", model="drift")]
+    table = TypeTable(rows)
+    rng = np.random.default_rng(8)
+    tid = rng.integers(0, 3, size=(n, m)).astype(np.uint8)
+    tid[rng.random((n, m)) < 0.1] = 255
+    speed = rng.uniform(3.0, 20.0, size=(n, m)).astype(np.float32)
+    w = BatchedWorld(n, m, table, device=cuda_device)
+    w.set_map(scene.segments, scene.bounds)
+    w.set_state(scene.x, scene.y, scene.heading, speed, type_id=tid)
+    w.set_wheel_state(speed / np.float32(0.344), speed / np.float32(0.344))
+    otab = table.as_oracle_table()
+    for t in range(4):
+        before = w.state_numpy()
+        act = synthetic.random_actions(70 + t, (n, m))
+        ref = O.physics_tick(before, tid, act, otab, 100, 5)
+        r = w.step(torch.from_numpy(act).to(cuda_device))
+        torch.cuda.synchronize()
+        got = w.state_numpy()
+        active = tid != 255
+        assert_state_close(got, ref, mask=active, rtol=1e-5, what=f"tick {t}")
+        drift = active & (tid >= 1)
+        for k in ("omega_wf", "omega_wr"):
+            assert rel_err(got[k], ref[k])[drift].max() < 1e-5
+            assert np.array_equal(got[k][~drift], before[k][~drift])     # nobody else's wheel state is touched
+        fl, hi, hs = O.events(got["x"], got["y"], got["heading"], tid, otab, scene.segments, scene.bounds)
+        assert np.array_equal(r.flags.cpu().numpy(), fl)
+        assert np.array_equal(r.hit_index.cpu().numpy(), hi)
+        assert np.array_equal(r.hit_segment.cpu().numpy(), hs)

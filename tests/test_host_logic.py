@@ -175,7 +175,7 @@ def test_type_table_and_c_layout():
     t = TypeTable.from_templates()
     assert len(t) == 16 and t.index("medium_car") == 2 and t.rows[12].shape == 1 and t.rows[9].lf == 0.9
     arr = t.to_c_array()
-    assert ctypes.sizeof(arr) == 16 * 76 and arr[2].accel_hi == np.float32(3.121)
+    assert ctypes.sizeof(arr) == 16 * 92 and arr[2].accel_hi == np.float32(3.121)
     o = t.as_oracle_table()
     assert o["half_len"][2] == np.float64(np.float32(2.142))
     with pytest.raises(ValueError):

@@ -159,3 +159,23 @@ def test_verify_state_golden():
            for r in g["inputs"]]
     assert np.array_equal(np.array(got), g["valid"])
     assert 0 < g["valid"].sum() < len(g["valid"])
+
+
+@pytest.mark.parametrize("name", ["con", "unc"])
+@pytest.mark.parametrize("interval,delta_t", [(100, 5), (9, 5), (50, 3)])
+def test_drift_restatement_equals_reference(name, interval, delta_t):
+    """SingleTrackDrift: two chained steps (the second consumes the wheel speeds of the first)."""
+    from oracle import physics as P
+
+    g = np.load(os.path.join(GOLD, "physics_drift.npz"))
+    inf = (-np.inf, np.inf)
+    rng = {k: (tuple(g[k]) if name == "con" else inf) for k in ("steer_range", "speed_range", "accel_range")}
+    st, om = g["states"], g["omega"]
+    want = g[f"drift_{name}_{interval}_{delta_t}"]
+    cur = dict(x=st[:, 0], y=st[:, 1], heading=st[:, 2], speed=st[:, 3], omega_wf=om[:, 0], omega_wr=om[:, 1])
+    for k, act in enumerate((g["actions"], g["actions2"])):
+        cur = P.step_drift(cur["x"], cur["y"], cur["heading"], cur["speed"], cur["omega_wf"], cur["omega_wr"], act[:, 0], act[:, 1],
+                           float(g["lf"]), float(g["lr"]), float(g["mass"]), 0.344, 0.76, 1.0, 1500.0, 1.7,
+                           rng["steer_range"], rng["speed_range"], rng["accel_range"], interval, delta_t)
+        got = np.stack([cur[f] for f in ("x", "y", "heading", "speed", "omega_wf", "omega_wr", "accel", "delta")], 1)
+        np.testing.assert_allclose(got, want[:, k], rtol=1e-9, atol=1e-9)
