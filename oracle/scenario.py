@@ -75,7 +75,8 @@ def physics_tick(state, type_id, action, table, interval=100, delta_t=5, steer_f
 
     def put(mask, res):
         for k in out:
-            out[k] = np.where(mask, res[k], out[k])
+            if k in res:          # only the drift model returns wheel speeds
+                out[k] = np.where(mask, res[k], out[k])
 
     m = active & (p["model"] == KINEMATICS)
     if m.any():
