@@ -183,12 +183,13 @@ __device__ __noinline__ void kin1_step(KinIO<1>& io, const Params& p, int n_step
   kinematics_step<1>(io, p1, n_steps, dt, dt_rem);
 }
 
-// Every model except the fp32 kinematic fast path (one copy of the fp64 code per kernel).
+// Every model except the fp32 kinematic fast path (one copy of the fp64 code per kernel).  SingleTrackDrift is NOT
+// integrated here: its fp64 tyre model needs far more registers than K1's budget (inlined, or even called, from K1 it
+// pushed the whole kernel into spilling and cost the other models 3 - 9 %), so t2d_drift_kernel advances those
+// participants in a pre-pass and K1 only builds their pose.
 __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem, double interval) {
   if (p.model == MODEL_DYNAMICS) {
     dynamics_step(io, p, n_steps, dt);
-  } else if (p.model == MODEL_DRIFT) {
-    drift_step(io, p, n_steps, dt, dt_rem);
   } else if (p.model == MODEL_POINTMASS_NEWTON) {
     pointmass_newton_step(io, p, interval);
   } else if (p.model == MODEL_POINTMASS_EULER) {
@@ -608,10 +609,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
             io.x = sx[i]; io.y = sy[i]; io.h = shd[i]; io.v = sv[i]; io.vx = svx[i]; io.vy = svy[i];
             io.a0 = a0[i]; io.a1 = a1[i];
             io.ch = 1.0f; io.sh = 0.0f;
-            const bool drift = pp[i]->model == MODEL_DRIFT;
-            if (drift) { io.w0 = A.wheel_f[idx0 + i]; io.w1 = A.wheel_r[idx0 + i]; }
             other_model_step(io, *pp[i], A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
-            if (drift) { A.wheel_f[idx0 + i] = io.w0; A.wheel_r[idx0 + i] = io.w1; }
             sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
             ch[i] = io.ch; sh[i] = io.sh;
           } else {
@@ -887,6 +885,28 @@ __global__ void t2d_reset_kernel(const __grid_constant__ ResetArgs A) {
 }
 
 // ---------------------------------------------------------------------------- K3
+// ---------------------------------------------------------------------------- drift pre-pass
+// SingleTrackDrift participants of a tick, one per thread, before K1 (which then only builds their pose).
+__global__ void __launch_bounds__(128) t2d_drift_kernel(const __grid_constant__ StepArgs A) {
+  const long long total = (long long)A.N * A.M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tid = A.type_id[i];
+    if (tid >= A.n_types) continue;
+    const Params& p = A.table[tid];
+    if (p.model != MODEL_DRIFT) continue;
+    OneIO io;
+    io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = 0.0f; io.vy = 0.0f;
+    const float2 act = reinterpret_cast<const float2*>(A.action)[i];
+    const bool sf = (A.cfg_flags & T2D_CFG_STEER_FIRST) != 0;
+    io.a0 = sf ? act.y : act.x; io.a1 = sf ? act.x : act.y;
+    io.ch = 1.0f; io.sh = 0.0f;
+    io.w0 = A.wheel_f[i]; io.w1 = A.wheel_r[i];
+    drift_step(io, p, A.n_steps, A.dt_d, A.dt_rem_d);
+    A.x[i] = io.x; A.y[i] = io.y; A.h[i] = io.h; A.v[i] = io.v; A.vx[i] = io.vx; A.vy[i] = io.vy;
+    A.wheel_f[i] = io.w0; A.wheel_r[i] = io.w1;
+  }
+}
+
 struct PhysArgs {
   Params p;
   float *x, *y, *h, *v, *vx, *vy;
@@ -913,10 +933,13 @@ __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant_
       io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = A.vx[i]; io.vy = A.vy[i];
       io.a0 = A.action[2 * i]; io.a1 = A.action[2 * i + 1];
       io.ch = 1.0f; io.sh = 0.0f;
-      const bool drift = A.p.model == MODEL_DRIFT;
-      if (drift) { io.w0 = A.wheel_f[i]; io.w1 = A.wheel_r[i]; }
-      other_model_step(io, A.p, A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
-      if (drift) { A.wheel_f[i] = io.w0; A.wheel_r[i] = io.w1; }
+      if (A.p.model == MODEL_DRIFT) {
+        io.w0 = A.wheel_f[i]; io.w1 = A.wheel_r[i];
+        drift_step(io, A.p, A.n_steps, A.dt_d, A.dt_rem_d);
+        A.wheel_f[i] = io.w0; A.wheel_r[i] = io.w1;
+      } else {
+        other_model_step(io, A.p, A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
+      }
       A.x[i] = io.x; A.y[i] = io.y; A.h[i] = io.h; A.v[i] = io.v; A.vx[i] = io.vx; A.vy[i] = io.vy;
       if (A.applied) { A.applied[2 * i] = io.a0; A.applied[2 * i + 1] = io.a1; }
     }
@@ -1585,7 +1608,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.max_step = c->cfg.max_step; A.cfg_flags = c->cfg.flags;
   A.do_physics = do_physics; A.has_bounds = c->has_bounds ? 1 : 0;
   A.bxmin = c->bounds[0]; A.bxmax = c->bounds[1]; A.bymin = c->bounds[2]; A.bymax = c->bounds[3];
-  A.needs_vel_in = c->has_pointmass ? 1 : 0;
+  A.needs_vel_in = (c->has_pointmass || c->has_drift) ? 1 : 0;   // (drift: K1 passes the pre-pass's vx, vy through)
   bool vec = (c->M % c->ppl == 0) && aligned16(A.x) && aligned16(A.y) && aligned16(A.h) && aligned16(A.v) && aligned16(A.vx) &&
              aligned16(A.vy) && (reinterpret_cast<uintptr_t>(A.type_id) % 4 == 0) && (!action || aligned16(action)) &&
              (!flags || reinterpret_cast<uintptr_t>(flags) % 4 == 0) && (!hit_index || reinterpret_cast<uintptr_t>(hit_index) % 8 == 0) &&
@@ -1642,6 +1665,13 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   if (smem > c->configured_smem) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->configured_smem = smem;
+  }
+  if (do_physics && c->has_drift) {
+    const long long total = (long long)count * c->M;
+    const int dgrid = (int)std::min<long long>((total + 127) / 128, (long long)c->sm_count * 16);
+    t2d_drift_kernel<<<dgrid, 128, 0, (cudaStream_t)stream>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
   }
   const long long ctas_needed = (tiles + wpc - 1) / wpc;
   if (c->occ_smem[wpc] != smem) {
@@ -1712,7 +1742,7 @@ int t2d_step_host(t2d_ctx* c, const float* action_host, uint8_t* flags, int16_t*
   int chunks = c->host_chunks;
   if (chunks <= 0) chunks = (int)std::min<long long>(t2d_ctx::MAX_HOST_CHUNKS, std::max<long long>(1, (long long)N * M / (1 << 20)));
   int per = (N + chunks - 1) / chunks;
-  per = (per + 15) & ~15;
+  per = (per + 31) & ~31;   // whole warp tiles (<= 32 scenarios per warp): a chunked tick groups lanes exactly as t2d_step does
   cudaStream_t s = (cudaStream_t)stream;
   const bool split = per < N;   // a single chunk needs no second stream
   if (split) {

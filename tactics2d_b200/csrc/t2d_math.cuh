@@ -225,7 +225,14 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
   // by e (two adds + two fmas; sin e = e and cos e - 1 = -e^2 / 2 to fp32 precision, products with e^2 dropped),
   // and drop the speed clamp and the running speed sum (closed form).  12 packed operations per pair of participants
   // and sub-step instead of 17 packed + 4 scalar.  The scalar and packed forms perform the same operations.
-  if (lin && small) {
+  // One loop per warp: lanes that could take the fast loop next to lanes that cannot would make the warp run both, so
+  // the warp takes it only when every lane that is executing this function can (the general loop is valid for all).
+#if defined(__CUDA_ARCH__)
+  const bool fast = __all_sync(__activemask(), lin && small);
+#else
+  const bool fast = lin && small;
+#endif
+  if (fast) {
     float h[W], nsn[W], se[W], nse[W], he[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
