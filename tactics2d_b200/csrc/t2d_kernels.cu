@@ -956,8 +956,9 @@ __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant_
 // < range) in shared memory in chunks, then every lane scans its beams (b = lane, lane + 32, ...) over the chunk.
 // fp64 throughout (from the fp32 state): the scan equals the float64 oracle to rounding, and B200 issues DFMA at
 // half the FFMA rate.
-constexpr int LIDAR_EDGES = 320;   // edges per shared-memory chunk per warp (4 doubles each)
+constexpr int LIDAR_EDGES = 144;   // edges per shared-memory chunk per warp (4 doubles + a beam window each)
 constexpr int LIDAR_WARPS = 4;
+constexpr int LIDAR_BEAMS = 512;   // beams per pass (running minima in shared memory)
 
 struct LidarArgs {
   const float *x, *y, *h;
@@ -980,13 +981,39 @@ __device__ __forceinline__ double point_segment_dist2(double x1, double y1, doub
   return ex * ex + ey * ey;
 }
 
-__global__ void __launch_bounds__(LIDAR_WARPS * 32) t2d_lidar_kernel(const __grid_constant__ LidarArgs A) {
+// Beam window of an edge.  The reference tests every (beam, edge) pair, but its filters (:201-209) keep an
+// intersection only if it lies on the edge (within 1e-8) AND on the beam's forward ray (within 2e-8 of the origin
+// side): a beam can score on an edge only if its direction falls inside the angle the edge subtends at the ego.  The
+// window is that angular interval widened by a whole beam on either side (the 1e-8 slacks are < 1e-5 rad beyond 1 cm
+// from the ego, atan2f is good to 1e-6 rad, beams are >= 1.7e-3 rad apart); edges that come within 1 cm of the ego, or
+// subtend nearly pi, get every beam.  Beams are uniformly spaced, theta_b = 2 pi b / n_beams (lidar.py:160).
+__device__ __forceinline__ int2 beam_window(double x1, double y1, double x2, double y2, double dist2, int n_beams) {
+  if (dist2 < 1e-4) return make_int2(0, n_beams);
+  const float a1 = atan2f((float)y1, (float)x1), a2 = atan2f((float)y2, (float)x2);
+  float diff = a2 - a1;
+  if (diff > 3.14159265f) diff -= 6.28318531f;
+  if (diff < -3.14159265f) diff += 6.28318531f;
+  if (fabsf(diff) > 3.0f) return make_int2(0, n_beams);
+  float start = diff >= 0.0f ? a1 : a2;
+  if (start < 0.0f) start += 6.28318531f;
+  const float inv = (float)n_beams * 0.159154943f;      // beams per radian
+  const int lo = (int)floorf(start * inv) - 1;
+  const int hi = (int)ceilf((start + fabsf(diff)) * inv) + 1;
+  const int cnt = min(hi - lo + 1, n_beams);
+  return make_int2(((lo % n_beams) + n_beams) % n_beams, cnt);
+}
+
+__global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __grid_constant__ LidarArgs A) {
   __shared__ double s_edge[LIDAR_WARPS][LIDAR_EDGES][4];
+  __shared__ int2 s_win[LIDAR_WARPS][LIDAR_EDGES];
+  __shared__ float s_best[LIDAR_WARPS][LIDAR_BEAMS];
   __shared__ int s_cnt[LIDAR_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n = (long long)blockIdx.x * LIDAR_WARPS + warp;
   if (n >= A.N) return;
   double(*edge)[4] = s_edge[warp];
+  int2* win = s_win[warp];
+  float* best = s_best[warp];
   int* cnt = &s_cnt[warp];
   const long long base = n * A.M;
   const int t_ego = A.type_id[base];
@@ -1000,80 +1027,94 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32) t2d_lidar_kernel(const __gri
   sincos(th, &sa, &ca);
   const double xoff = -x0 * ca - y0 * sa, yoff = x0 * sa - y0 * ca;   // lidar.py:116-121
   const double R = A.range, R2 = R * R;
-  // beams of this lane: running minimum of the squared distance
-  constexpr int MAXB = 16;   // beams per lane handled in registers per pass (n_beams <= 512 per pass)
-  const int n_edges_part = (A.M - 1) * 4;
   const float4* seg = A.map_blob ? reinterpret_cast<const float4*>(A.map_blob + A.mh.off_seg) : nullptr;
   const int n_seg = A.map_blob ? A.mh.n_seg : 0;
-  const int total_src = n_edges_part + n_seg;
-  for (int b0 = 0; b0 < A.n_beams; b0 += 32 * MAXB) {
-    double best[MAXB];
+  const int part_rounds = (A.M - 1 + 31) / 32, seg_rounds = (n_seg + 31) / 32;
+  for (int b0 = 0; b0 < A.n_beams; b0 += LIDAR_BEAMS) {
+    const int nb = min(LIDAR_BEAMS, A.n_beams - b0);      // beams b0 .. b0 + nb - 1 in this pass
+    for (int k = lane; k < nb; k += 32) best[k] = INFINITY;
+    if (lane == 0) *cnt = 0;
+    __syncwarp();
+    // Sources in rounds of 32: the other participants (a cheap centre-distance test first; a box in reach contributes
+    // its four ring edges, :146-153), then the map segments (:137-143).  Edges within the range go to the shared chunk
+    // with their beam window; the chunk is scanned whenever the next round might not fit.
+    for (int r = 0; r < part_rounds + seg_rounds; ++r) {
+      if (r < part_rounds) {
+        const int j = 1 + r * 32 + lane;
+        const int tj = j < A.M ? (int)A.type_id[base + j] : 255;
+        if (tj < A.n_types && A.table[tj].shape == SHAPE_OBB) {
+          const Params& pj = A.table[tj];
+          const double xj = A.x[base + j], yj = A.y[base + j];
+          const double reach = R + (double)pj.rbound * 1.000001 + 1e-6;
+          if ((xj - x0) * (xj - x0) + (yj - y0) * (yj - y0) <= reach * reach) {
+            double cx[4], cy[4], ex[4], ey[4];
+            rect_corners_f64(xj, yj, A.h[base + j], pj.half_len, pj.half_wid, cx, cy);
 #pragma unroll
-    for (int k = 0; k < MAXB; ++k) best[k] = INFINITY;
-    for (int src0 = 0; src0 < total_src; src0 += LIDAR_EDGES) {
-      // ---- stage one chunk of candidate edges (ego frame), compacted
-      if (lane == 0) *cnt = 0;
-      __syncwarp();
-      const int src1 = min(src0 + LIDAR_EDGES, total_src);
-      for (int e = src0 + lane; e < src1; e += 32) {
-        double gx1, gy1, gx2, gy2;
-        bool ok = true;
-        if (e < n_edges_part) {
-          const int j = 1 + e / 4, k = e & 3;
-          const int tj = A.type_id[base + j];
-          ok = tj < A.n_types && A.table[tj].shape == SHAPE_OBB;
-          if (ok) {
-            double cx[4], cy[4];
-            rect_corners_f64(A.x[base + j], A.y[base + j], A.h[base + j], A.table[tj].half_len, A.table[tj].half_wid, cx, cy);
-            gx1 = cx[k]; gy1 = cy[k]; gx2 = cx[(k + 1) & 3]; gy2 = cy[(k + 1) & 3];
+            for (int k = 0; k < 4; ++k) {   // affine [a, b, -b, a, xoff, yoff]
+              ex[k] = ca * cx[k] + sa * cy[k] + xoff;
+              ey[k] = -sa * cx[k] + ca * cy[k] + yoff;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const double x1 = ex[k], y1 = ey[k], x2 = ex[(k + 1) & 3], y2 = ey[(k + 1) & 3];
+              const double d2 = point_segment_dist2(x1, y1, x2, y2);
+              if (d2 < R2 * 1.0000001 + 1e-9) {
+                const int slot = atomicAdd(cnt, 1);
+                edge[slot][0] = x1; edge[slot][1] = y1; edge[slot][2] = x2; edge[slot][3] = y2;
+                win[slot] = beam_window(x1, y1, x2, y2, d2, A.n_beams);
+              }
+            }
           }
-        } else {
-          const float4 sg = seg[e - n_edges_part];
-          gx1 = sg.x; gy1 = sg.y; gx2 = sg.z; gy2 = sg.w;
         }
-        if (ok) {
-          const double x1 = ca * gx1 + sa * gy1 + xoff, y1 = -sa * gx1 + ca * gy1 + yoff;   // affine [a, b, -b, a, xoff, yoff]
-          const double x2 = ca * gx2 + sa * gy2 + xoff, y2 = -sa * gx2 + ca * gy2 + yoff;
-          if (point_segment_dist2(x1, y1, x2, y2) < R2 * 1.0000001 + 1e-9) {
+      } else {
+        const int si = (r - part_rounds) * 32 + lane;
+        if (si < n_seg) {
+          const float4 sg = seg[si];
+          const double x1 = ca * sg.x + sa * sg.y + xoff, y1 = -sa * sg.x + ca * sg.y + yoff;
+          const double x2 = ca * sg.z + sa * sg.w + xoff, y2 = -sa * sg.z + ca * sg.w + yoff;
+          const double d2 = point_segment_dist2(x1, y1, x2, y2);
+          if (d2 < R2 * 1.0000001 + 1e-9) {
             const int slot = atomicAdd(cnt, 1);
             edge[slot][0] = x1; edge[slot][1] = y1; edge[slot][2] = x2; edge[slot][3] = y2;
+            win[slot] = beam_window(x1, y1, x2, y2, d2, A.n_beams);
           }
         }
       }
       __syncwarp();
       const int n_e = *cnt;
-      // ---- scan the beams of this lane over the chunk (lidar.py:160-213)
+      if (n_e + 128 <= LIDAR_EDGES && r + 1 < part_rounds + seg_rounds) continue;   // the next round still fits
+      // ---- edge by edge, the lanes share the beams of its window (lidar.py:160-213 for those pairs)
       for (int i = 0; i < n_e; ++i) {
         const double x1 = edge[i][0], y1 = edge[i][1], x2 = edge[i][2], y2 = edge[i][3];
+        const int2 w = win[i];
         const double d = y2 - y1, e = x1 - x2, f = y1 * x2 - x1 * y2;
         const double xlo = fmin(x1, x2) - 1e-8, xhi = fmax(x1, x2) + 1e-8, ylo = fmin(y1, y2) - 1e-8, yhi = fmax(y1, y2) + 1e-8;
-#pragma unroll
-        for (int k = 0; k < MAXB; ++k) {
-          const int b = b0 + lane + 32 * k;
-          if (b < A.n_beams) {
-            const double cb = A.beam_cs[2 * b], sb = A.beam_cs[2 * b + 1];
-            const double a_ = sb, b_ = -cb;
-            const double det = a_ * e - b_ * d;
-            if (det != 0.0) {
-              const double rx = (b_ * f) / det, ry = (-a_ * f) / det;
-              const double lx = cb * R, ly = sb * R;
-              const bool okx = !(rx > fmax(1e-8, lx) + 1e-8) && !(rx < fmin(-1e-8, lx) - 1e-8) && !(rx > xhi) && !(rx < xlo);
-              const bool oky = !(ry > fmax(1e-8, ly) + 1e-8) && !(ry < fmin(-1e-8, ly) - 1e-8) && !(ry > yhi) && !(ry < ylo);
-              if (okx && oky) best[k] = fmin(best[k], rx * rx + ry * ry);
+        for (int t = lane; t < w.y; t += 32) {
+          int b = w.x + t;
+          if (b >= A.n_beams) b -= A.n_beams;
+          const int k = b - b0;
+          if (k < 0 || k >= nb) continue;
+          const double cb = A.beam_cs[2 * b], sb = A.beam_cs[2 * b + 1];
+          const double a_ = sb, b_ = -cb;
+          const double det = a_ * e - b_ * d;
+          if (det != 0.0) {
+            const double rx = (b_ * f) / det, ry = (-a_ * f) / det;
+            const double lx = cb * R, ly = sb * R;
+            const bool okx = !(rx > fmax(1e-8, lx) + 1e-8) && !(rx < fmin(-1e-8, lx) - 1e-8) && !(rx > xhi) && !(rx < xlo);
+            const bool oky = !(ry > fmax(1e-8, ly) + 1e-8) && !(ry < fmin(-1e-8, ly) - 1e-8) && !(ry > yhi) && !(ry < ylo);
+            if (okx && oky) {
+              const double dist = sqrt(rx * rx + ry * ry);
+              if (dist < R) best[k] = fminf(best[k], (float)dist);   // clip to the range, range -> inf (:211-213)
             }
           }
         }
+        __syncwarp();   // the next edge's window may hand the same beam to another lane
       }
+      if (lane == 0) *cnt = 0;
       __syncwarp();
     }
-#pragma unroll
-    for (int k = 0; k < MAXB; ++k) {
-      const int b = b0 + lane + 32 * k;
-      if (b < A.n_beams) {
-        const double dist = sqrt(best[k]);
-        out[b] = dist < R ? (float)dist : INFINITY;   // clip to the range, range -> inf (:211-213)
-      }
-    }
+    for (int k = lane; k < nb; k += 32) out[b0 + k] = best[k];
+    __syncwarp();
   }
 }
 

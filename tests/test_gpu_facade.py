@@ -311,6 +311,31 @@ def test_batched_env_with_targets_terminates_on_arrival(cuda_device):
     env.close()
 
 
+def test_lidar_scan_dense_scene_and_many_beams(cuda_device):
+    """Beam-window culling edge cases: vehicles overlapping / touching the ego (edges through the sensor origin get every
+    beam), windows that wrap around beam 0, more beams than one shared-memory pass holds."""
+    from oracle import lidar as OL
+    from tactics2d_b200 import BatchedWorld, synthetic
+
+    n, m, n_beams, max_range = 24, 24, 1100, 9.0
+    scene = synthetic.config4(n, m, seed=13, size=18.0, segments=synthetic.grid_wall_segments(18.0, 9.0, 5.0))
+    scene.type_id[:, :2] = 2          # ego and its closest neighbour are medium cars
+    # put participant 1 right on top of the ego in a few scenarios, and exactly corner-to-corner in others
+    scene.x[:4, 1], scene.y[:4, 1] = scene.x[:4, 0] + 0.3, scene.y[:4, 0] - 0.2
+    scene.x[4:8, 1], scene.y[4:8, 1] = scene.x[4:8, 0], scene.y[4:8, 0]
+    w = BatchedWorld(n, m, scene.table, device=cuda_device)
+    w.set_map(scene.segments, scene.bounds)
+    w.set_state(scene.x, scene.y, scene.heading, scene.speed, type_id=scene.type_id)
+    got = w.lidar_scan(n_beams, max_range).cpu().numpy().astype(np.float64)
+    ref = OL.scan_world(scene.x.astype(np.float64), scene.y.astype(np.float64), scene.heading.astype(np.float64), scene.type_id,
+                        scene.table.as_oracle_table(), scene.segments, n_beams, max_range)
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    hit = np.isfinite(ref)
+    assert hit.mean() > 0.5
+    assert np.abs(got[hit] - ref[hit]).max() < 2e-6 * max_range + 1e-6
+    w.close()
+
+
 @pytest.mark.parametrize("n_beams,max_range", [(360, 20.0), (500, 12.0), (37, 30.0)])
 def test_lidar_scan_matches_reference_restatement(cuda_device, n_beams, max_range):
     """SingleLineLidar._scan_obstacles for every ego against the NumPy restatement (oracle/lidar.py): same hit / no-hit
