@@ -952,10 +952,10 @@ __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant_
 // exteriors of `area.type_ == "obstacle"`, :137-143) + the pose rings of the other box-shaped participants (:146-153;
 // a Pedestrian's pose is not a ring and is skipped there too), transformed into the ego frame (:105-126); per beam
 // the reference's determinant intersection with its 1e-8 slack box filters (:160-213), min over edges, clip to the
-// range, range -> inf.  One warp per scenario: the warp stages the edges that can matter (distance to the ego
-// < range) in shared memory in chunks, then every lane scans its beams (b = lane, lane + 32, ...) over the chunk.
-// fp64 throughout (from the fp32 state): the scan equals the float64 oracle to rounding, and B200 issues DFMA at
-// half the FFMA rate.
+// range, range -> inf.  One warp per scenario: sources are culled by distance, the surviving edges go to shared memory
+// together with their beam window (beam_window below), and the warp walks the edges with its lanes sharing the beams of
+// each window.  fp64 throughout (from the fp32 state): every tested pair gives exactly the float64 oracle's value, the
+// untested pairs are ones the reference's own filters reject.
 constexpr int LIDAR_EDGES = 144;   // edges per shared-memory chunk per warp (4 doubles + a beam window each)
 constexpr int LIDAR_WARPS = 4;
 constexpr int LIDAR_BEAMS = 512;   // beams per pass (running minima in shared memory)
