@@ -248,6 +248,16 @@ def run_ours(args):
         pools.append({k: getattr(w, k).clone() for k in ("x", "y", "heading", "speed", "vx", "vy")})
     ones = torch.ones(n, dtype=torch.uint8, device=device)
     done_all = torch.zeros(world_size * n, dtype=torch.uint8, device=device) if world_size > 1 else None
+    # The one exchange of the path: every rank gets every rank's done mask of each step.  Default: the tick stores the
+    # done bytes into every rank's gather buffer itself (peer memory) and a one-CTA kernel on a side stream completes the
+    # gather; --exchange nccl uses all_gather_into_tensor instead.
+    peer = None
+    if world_size > 1 and args.exchange == "peer":
+        from tactics2d_b200.distributed import PeerDoneExchange
+
+        peer = PeerDoneExchange(n, device, slots=8)
+        for w in worlds:
+            peer.attach(w)
 
     def restore():
         for w, p in zip(worlds, pools):
@@ -258,21 +268,32 @@ def run_ours(args):
     # it; a learner / reset scheduler does); the streams are joined before the timed region ends.
     comm_stream = torch.cuda.Stream(device) if world_size > 1 else None
 
+    gathered_ev = {}
+
     def one_step(i):
         r = i % R
+        main = torch.cuda.current_stream(device)
+        if peer is not None and i - 3 in gathered_ev:
+            main.wait_event(gathered_ev.pop(i - 3))   # ring of 8 slots: never tick more than 3 steps past our own gather
         out = worlds[r].step(actions[r])
         if world_size > 1:
-            main = torch.cuda.current_stream(device)
             ev = torch.cuda.Event()
             ev.record(main)
             comm_stream.wait_event(ev)
             with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(done_all, out.done)
+                if peer is not None:
+                    peer.gather(done_all)
+                    g = torch.cuda.Event()
+                    g.record(comm_stream)
+                    gathered_ev[i] = g
+                else:
+                    dist.all_gather_into_tensor(done_all, out.done)
         return out
 
     def join_comm():
         if world_size > 1:
             torch.cuda.current_stream(device).wait_stream(comm_stream)
+            gathered_ev.clear()
 
     def barrier():
         torch.cuda.synchronize()
@@ -363,12 +384,15 @@ def run_ours(args):
             def e2e_step(i):
                 dev_act.copy_(host_act[i % len(host_act)], non_blocking=True)
                 out = worlds[i % R].step(dev_act)
-                dist.all_gather_into_tensor(done_all, out.done)
+                if peer is not None:
+                    peer.gather(done_all)
+                else:
+                    dist.all_gather_into_tensor(done_all, out.done)
                 host_done.copy_(out.done, non_blocking=True)
                 host_status.copy_(out.status, non_blocking=True)
                 stream.synchronize()   # the caller reads done/status before choosing the next action
-            api = ("BatchedWorld.step(action) with pinned-host action -> device copy, all_gather(done), done/status -> "
-                   "pinned-host copy, stream sync per step")
+            api = ("BatchedWorld.step(action) with pinned-host action -> device copy, done-mask exchange (" + args.exchange +
+                   "), done/status -> pinned-host copy, stream sync per step")
 
         restore()
         for i in range(W):
@@ -411,7 +435,9 @@ def run_ours(args):
                        "l2_policy": f"inputs larger than L2: {R} world replicas x {bytes_per_launch / 1e6:.1f} MB rotate through the timed steps ({R * bytes_per_launch / 1e6:.0f} MB > {l2_bytes / 1e6:.0f} MB L2)",
                        "timed_region": "CUDA graph of K steps" if graph is not None else "eager launch loop of K steps",
                        "reps": len(reps_ms), "rep_ms_min": min(reps_ms), "rep_ms_max": max(reps_ms),
-                       "collective": "all_gather(done) per step (NCCL, side stream, overlaps the next tick)" if world_size > 1 else "none (1 GPU)"},
+                       "collective": ("none (1 GPU)" if world_size == 1 else
+                                      "done mask per step: peer stores from inside the tick + one-CTA gather kernel on a side stream (t2d_exchange_*)" if peer is not None else
+                                      "all_gather(done) per step (NCCL, side stream, overlaps the next tick)")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "t2d_step_kernel",
@@ -431,6 +457,12 @@ def run_ours(args):
             except Exception as e:
                 line["cpu_baseline_compiled"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        published, gathered, timed_out = peer.status()
+        if timed_out or published != gathered:
+            print(f"[bench] rank {rank}: done exchange inconsistent: published {published} gathered {gathered} timed_out {timed_out}",
+                  file=sys.stderr)
+            os._exit(3)
     if world_size > 1:
         # leave without tearing NCCL down under a live CUDA graph that captured its collectives (that teardown
         # can dead-lock): drop the graph, drain the device, meet the other ranks, then exit hard.
@@ -451,6 +483,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer", help="N > 1: how the done masks are exchanged")
     ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -81,6 +81,13 @@ struct StepArgs {
   int goal_noact_max;
   long long* dbg_clock;            // optional [n_tiles][8] phase time stamps (T2D_DEBUG_CLOCK); nullptr in production
   float *wheel_f, *wheel_r;        // [N][M] wheel angular speeds of the SingleTrackDrift participants, or nullptr
+  // done-mask exchange over peer memory (t2d_exchange_*): every rank's K1 stores its done bytes straight into every
+  // rank's gather buffer; the last CTA to finish publishes the step on every rank's flag word
+  int xchg_world, xchg_rank, xchg_slots, xchg_first;   // xchg_first: offset of this launch's scenarios in the rank's block
+  int xchg_n_local;
+  unsigned char* xchg_peer[T2D_MAX_RANKS];             // base of every rank's exchange allocation (own included)
+  unsigned* xchg_epoch;                                // local: steps published so far
+  unsigned* xchg_arrive;                               // local: CTAs that finished this launch
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -474,6 +481,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
   // ... and wait here, before the first access to the state the previous tick wrote, until that grid has
   // completed and flushed (no-op when the kernel was not launched as a programmatic dependent).
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // step number of this launch for the done exchange: the previous launch (complete by now) left it in xchg_epoch,
+  // and this launch's last CTA bumps it only after every CTA has passed its final barrier
+  const unsigned xchg_step = A.xchg_world ? *reinterpret_cast<volatile unsigned*>(A.xchg_epoch) : 0u;
 
   const int G = A.G, M = A.M;
   const int spw = 32 >> A.g_shift;      // scenarios per warp
@@ -839,6 +849,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         if (A.max_step > 0 && cnt > A.max_step) st = T2D_STATUS_TIME_EXCEEDED;  // parking.py:366-369
         if (A.scn_status) A.scn_status[n] = st;
         if (A.done) A.done[n] = st != T2D_STATUS_NORMAL;             // parking.py:243-248
+        if (A.xchg_world) {   // the same byte into slot (step mod slots) of every rank's gather buffer, over NVLink
+          const size_t off = (size_t)(xchg_step % (unsigned)A.xchg_slots) * A.xchg_world * A.xchg_n_local +
+                             (size_t)A.xchg_rank * A.xchg_n_local + A.xchg_first + n;
+          const unsigned char v = st != T2D_STATUS_NORMAL;
+          for (int p = 0; p < A.xchg_world; ++p) A.xchg_peer[p][off] = v;
+        }
       }
     }
     T2D_STAMP(7);
@@ -851,6 +867,25 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     __syncwarp();   // pose tile is reused by the next tile
   }
   if (!staged) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
+  if (A.xchg_world && A.do_physics) {
+    // Publish the step: every CTA fences its peer stores to system scope and counts itself in; the last one
+    // writes (step + 1) into slot `rank` of every rank's flag array with release semantics and opens the next step.
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const unsigned arrived = atomicAdd(A.xchg_arrive, 1u);
+      if (arrived == gridDim.x - 1) {
+        *A.xchg_arrive = 0u;
+        __threadfence_system();
+        const size_t flag_off = (size_t)A.xchg_slots * A.xchg_world * A.xchg_n_local;   // flags follow the slots (16 B aligned)
+        for (int p = 0; p < A.xchg_world; ++p) {
+          unsigned* f = reinterpret_cast<unsigned*>(A.xchg_peer[p] + flag_off) + A.xchg_rank;
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(xchg_step + 1u) : "memory");
+        }
+        *reinterpret_cast<volatile unsigned*>(A.xchg_epoch) = xchg_step + 1u;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------- K2
@@ -1118,6 +1153,52 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __
   }
 }
 
+// ============================================================================ done exchange: consumer side
+// One CTA: lanes 0 .. world-1 of warp 0 wait (acquire, system scope) until every rank has published the oldest step
+// this rank has not gathered yet, then the CTA copies that step's slot - all ranks' done masks, in rank order - into
+// dst.  The spin is bounded (about two seconds of SM clocks); on expiry the error word is set and the copy is skipped.
+struct GatherArgs {
+  const unsigned char* base;     // local exchange allocation
+  unsigned* gathered;            // local: steps gathered so far
+  unsigned* error;               // local: sticky time-out flag
+  unsigned char* dst;            // [world * n_local]
+  int world, n_local, slots;
+};
+
+__global__ void __launch_bounds__(256) t2d_exchange_gather_kernel(const __grid_constant__ GatherArgs A) {
+  __shared__ int s_ok;
+  const unsigned want = *A.gathered + 1u;
+  const size_t flag_off = (size_t)A.slots * A.world * A.n_local;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < (unsigned)A.world) {
+    const unsigned* f = reinterpret_cast<const unsigned*>(A.base + flag_off) + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v >= want) break;
+      if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (!s_ok) {
+    if (threadIdx.x == 0) *A.error = 1u;
+    return;
+  }
+  const size_t bytes = (size_t)A.world * A.n_local;
+  const unsigned char* src = A.base + (size_t)((want - 1u) % (unsigned)A.slots) * bytes;
+  if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(A.dst) & 15) == 0) {
+    for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(A.dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+  } else {
+    for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) A.dst[i] = src[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *A.gathered = want;
+}
+
 // ============================================================================ K5: NPC controllers
 // One warp per scenario; lane l owns participants l, l + 32, ... .  fp64 on the fp32 state (a few dozen flops per
 // participant: the kernel is bound by its ~30 B / participant of HBM traffic).  All reads of last_accel (own and the
@@ -1289,10 +1370,21 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess) return fail(T2D_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+struct t2d_exchange {
+  int device = 0, world = 0, rank = 0, n_local = 0, slots = 0;
+  size_t bytes = 0;
+  unsigned char* base = nullptr;                 // slots x world x n_local done bytes | world flags | epoch, arrive, gathered, error
+  unsigned char* peer[T2D_MAX_RANKS] = {};       // every rank's base (own included), valid after t2d_exchange_connect
+  bool connected = false;
+  size_t flag_off() const { return (size_t)slots * world * n_local; }
+  unsigned* word(int i) const { return reinterpret_cast<unsigned*>(base + flag_off()) + T2D_MAX_RANKS + i; }   // 0 epoch, 1 arrive, 2 gathered, 3 error
+};
+
 struct t2d_ctx {
   int device = 0, N = 0, M = 0, G = 0, ppl = 4;
   t2d_config cfg{};
   int n_types = 0;
+  t2d_exchange* xchg = nullptr;
   bool has_pointmass = false;
   bool has_drift = false;
   bool kin_only = false;
@@ -1656,6 +1748,15 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
              (!hit_segment || reinterpret_cast<uintptr_t>(hit_segment) % 8 == 0);
   A.vec_ok = vec ? 1 : 0;
 
+  if (c->xchg && do_physics) {
+    const t2d_exchange* x = c->xchg;
+    if (!x->connected) return fail(T2D_E_STATE, "exchange attached but not connected: call t2d_exchange_connect first");
+    if (x->n_local < c->N) return fail(T2D_E_INVALID, "exchange was created for fewer scenarios per rank");
+    if (first != 0 || count != c->N) return fail(T2D_E_UNSUPPORTED, "the done exchange publishes whole ticks: not available through t2d_step_host chunks");
+    A.xchg_world = x->world; A.xchg_rank = x->rank; A.xchg_slots = x->slots; A.xchg_first = first; A.xchg_n_local = x->n_local;
+    for (int p = 0; p < x->world; ++p) A.xchg_peer[p] = x->peer[p];
+    A.xchg_epoch = x->word(0); A.xchg_arrive = x->word(1);
+  }
   A.rb_max = c->rb_max;
   A.dbg_clock = c->dbg_clock;
   A.goal_target = c->goal_target ? c->goal_target + 5 * (size_t)first : nullptr;
@@ -1933,6 +2034,88 @@ int t2d_control(t2d_ctx* c, float* action, void* stream) {
   t2d_control_kernel<<<grid, warps_per_cta * 32, 0, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int n_local, int slots, void* ipc_handle_out) {
+  if (!out || !ipc_handle_out) return fail(T2D_E_INVALID, "out / ipc_handle_out is NULL");
+  *out = nullptr;
+  if (world < 1 || world > T2D_MAX_RANKS || rank < 0 || rank >= world) return fail(T2D_E_INVALID, "bad world / rank");
+  if (n_local <= 0 || slots < 2 || slots > 64) return fail(T2D_E_INVALID, "n_local must be > 0 and slots in 2..64");
+  static_assert(sizeof(cudaIpcMemHandle_t) == T2D_IPC_HANDLE_BYTES, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(device));
+  t2d_exchange* x = new t2d_exchange();
+  x->device = device; x->world = world; x->rank = rank; x->n_local = (n_local + 15) & ~15; x->slots = slots;
+  x->bytes = x->flag_off() + (T2D_MAX_RANKS + 4) * sizeof(unsigned);
+  cudaError_t e = cudaMalloc(&x->base, x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->base);
+  if (e != cudaSuccess) {
+    if (x->base) cudaFree(x->base);
+    delete x;
+    return fail(T2D_E_CUDA, std::string("t2d_exchange_create: ") + cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = x;
+  return T2D_OK;
+}
+
+int t2d_exchange_connect(t2d_exchange* x, const void* handles) {
+  if (!x || !handles) return fail(T2D_E_INVALID, "exchange / handles is NULL");
+  CUDA_TRY(cudaSetDevice(x->device));
+  for (int p = 0; p < x->world; ++p) {
+    if (p == x->rank) { x->peer[p] = x->base; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)p * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peer[p] = static_cast<unsigned char*>(ptr);
+  }
+  x->connected = true;
+  return T2D_OK;
+}
+
+int t2d_exchange_attach(t2d_ctx* c, t2d_exchange* x) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (x && x->device != c->device) return fail(T2D_E_INVALID, "exchange lives on another device");
+  if (x && x->n_local < c->N) return fail(T2D_E_INVALID, "exchange holds fewer scenarios per rank than the context");
+  c->xchg = x;
+  return T2D_OK;
+}
+
+int t2d_exchange_gather(t2d_exchange* x, uint8_t* dst, void* stream) {
+  if (!x || !dst) return fail(T2D_E_INVALID, "exchange / dst is NULL");
+  if (!x->connected) return fail(T2D_E_STATE, "exchange not connected");
+  CUDA_TRY(cudaSetDevice(x->device));
+  GatherArgs A{};
+  A.base = x->base; A.gathered = x->word(2); A.error = x->word(3); A.dst = dst;
+  A.world = x->world; A.n_local = x->n_local; A.slots = x->slots;
+  t2d_exchange_gather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
+int t2d_exchange_status(t2d_exchange* x, uint32_t* published, uint32_t* gathered, uint32_t* timed_out) {
+  if (!x) return fail(T2D_E_INVALID, "exchange is NULL");
+  CUDA_TRY(cudaSetDevice(x->device));
+  unsigned w[4];
+  CUDA_TRY(cudaMemcpy(w, x->word(0), sizeof(w), cudaMemcpyDeviceToHost));
+  if (published) *published = w[0];
+  if (gathered) *gathered = w[2];
+  if (timed_out) *timed_out = w[3];
+  return T2D_OK;
+}
+
+int t2d_exchange_destroy(t2d_exchange* x) {
+  if (!x) return T2D_OK;
+  cudaSetDevice(x->device);
+  for (int p = 0; p < x->world; ++p)
+    if (x->connected && p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
+  if (x->base) cudaFree(x->base);
+  delete x;
   return T2D_OK;
 }
 
