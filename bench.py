@@ -248,16 +248,14 @@ def run_ours(args):
         pools.append({k: getattr(w, k).clone() for k in ("x", "y", "heading", "speed", "vx", "vy")})
     ones = torch.ones(n, dtype=torch.uint8, device=device)
     done_all = torch.zeros(world_size * n, dtype=torch.uint8, device=device) if world_size > 1 else None
-    # The one exchange of the path: every rank gets every rank's done mask of each step.  Default: the tick stores the
-    # done bytes into every rank's gather buffer itself (peer memory) and a one-CTA kernel on a side stream completes the
-    # gather; --exchange nccl uses all_gather_into_tensor instead.
+    # The one exchange of the path: every rank gets every rank's done mask of each step.  Default: our own all-gather
+    # kernel over peer memory (t2d_exchange_allgather: put to every rank, signal, wait, copy - one CTA per rank and step);
+    # --exchange nccl uses all_gather_into_tensor instead.  Either runs on a side stream under the next tick.
     peer = None
     if world_size > 1 and args.exchange == "peer":
         from tactics2d_b200.distributed import PeerDoneExchange
 
-        peer = PeerDoneExchange(n, device, slots=8)
-        for w in worlds:
-            peer.attach(w)
+        peer = PeerDoneExchange(n, device, slots=4)
 
     def restore():
         for w, p in zip(worlds, pools):
@@ -268,24 +266,17 @@ def run_ours(args):
     # it; a learner / reset scheduler does); the streams are joined before the timed region ends.
     comm_stream = torch.cuda.Stream(device) if world_size > 1 else None
 
-    gathered_ev = {}
-
     def one_step(i):
         r = i % R
-        main = torch.cuda.current_stream(device)
-        if peer is not None and i - 3 in gathered_ev:
-            main.wait_event(gathered_ev.pop(i - 3))   # ring of 8 slots: never tick more than 3 steps past our own gather
         out = worlds[r].step(actions[r])
         if world_size > 1:
+            main = torch.cuda.current_stream(device)
             ev = torch.cuda.Event()
             ev.record(main)
             comm_stream.wait_event(ev)
             with torch.cuda.stream(comm_stream):
                 if peer is not None:
-                    peer.gather(done_all)
-                    g = torch.cuda.Event()
-                    g.record(comm_stream)
-                    gathered_ev[i] = g
+                    peer(out.done, done_all)
                 else:
                     dist.all_gather_into_tensor(done_all, out.done)
         return out
@@ -293,7 +284,6 @@ def run_ours(args):
     def join_comm():
         if world_size > 1:
             torch.cuda.current_stream(device).wait_stream(comm_stream)
-            gathered_ev.clear()
 
     def barrier():
         torch.cuda.synchronize()
@@ -385,7 +375,7 @@ def run_ours(args):
                 dev_act.copy_(host_act[i % len(host_act)], non_blocking=True)
                 out = worlds[i % R].step(dev_act)
                 if peer is not None:
-                    peer.gather(done_all)
+                    peer(out.done, done_all)
                 else:
                     dist.all_gather_into_tensor(done_all, out.done)
                 host_done.copy_(out.done, non_blocking=True)
@@ -436,7 +426,7 @@ def run_ours(args):
                        "timed_region": "CUDA graph of K steps" if graph is not None else "eager launch loop of K steps",
                        "reps": len(reps_ms), "rep_ms_min": min(reps_ms), "rep_ms_max": max(reps_ms),
                        "collective": ("none (1 GPU)" if world_size == 1 else
-                                      "done mask per step: peer stores from inside the tick + one-CTA gather kernel on a side stream (t2d_exchange_*)" if peer is not None else
+                                      "all-gather(done) per step by our own peer-memory kernel (t2d_exchange_allgather: put, signal, wait, copy), side stream, overlaps the next tick" if peer is not None else
                                       "all_gather(done) per step (NCCL, side stream, overlaps the next tick)")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -458,10 +448,10 @@ def run_ours(args):
                 line["cpu_baseline_compiled"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if peer is not None:
-        published, gathered, timed_out = peer.status()
-        if timed_out or published != gathered:
-            print(f"[bench] rank {rank}: done exchange inconsistent: published {published} gathered {gathered} timed_out {timed_out}",
-                  file=sys.stderr)
+        torch.cuda.synchronize()
+        steps_done, timed_out = peer.status()
+        if timed_out:
+            print(f"[bench] rank {rank}: the done exchange timed out ({steps_done} steps exchanged)", file=sys.stderr)
             os._exit(3)
     if world_size > 1:
         # leave without tearing NCCL down under a live CUDA graph that captured its collectives (that teardown

@@ -246,26 +246,21 @@ int t2d_control(t2d_ctx* ctx, float* action, void* stream);
 /* ---- done-mask exchange across the GPUs of one node, over peer memory (NVLink / NVSwitch) -------------------------
  * Scenarios are sharded across ranks (one process per GPU); the one exchange of the path is "every rank learns every
  * rank's done mask of this tick" - the terminated / truncated vector a central learner or reset scheduler reads
- * (envs/parking.py:243-248 per scenario).  Instead of a collective after the tick, t2d_step itself stores each done
- * byte into a gather buffer on EVERY rank (peer stores) and its last CTA publishes the step number on every rank's
- * flag word; t2d_exchange_gather waits for all ranks' flags of the oldest ungathered step and copies that step's
- * [world * n_local] mask (rank order) into the caller's array.
+ * (envs/parking.py:243-248 per scenario).  t2d_exchange_allgather is that all-gather as ONE small kernel per rank:
+ * it stores the rank's mask into a ring slot on EVERY rank (peer stores), signals the step on every rank's flag word
+ * (release, system scope), waits for all ranks' signals of the same step (acquire; bounded - a rank that never shows
+ * up sets the sticky timed_out word instead of hanging the GPU) and copies the slot to the caller's array.
  *
- * Set-up: every rank calls t2d_exchange_create (fills a 64-byte CUDA IPC handle), the ranks all-gather the handles by
- * any host channel (torch.distributed in this repository), every rank calls t2d_exchange_connect with all `world`
- * handles in rank order, then t2d_exchange_attach on each context that should publish.  n_local = scenarios per rank
- * (rounded up to 16 inside); slots = ring depth: the mask of step s lives in slot s % slots until step s + slots
- * overwrites it, so a rank may run at most slots - 1 ticks ahead of the slowest gather on any rank - the caller
- * orders tick s after its own gather of step s - slots / 2 at the latest (bench.py uses 8 slots and distance 3).
- * All ranks must tick in the same order; t2d_step_host (chunked ticks) does not publish. */
+ * Set-up: every rank calls t2d_exchange_create (fills a 64-byte CUDA IPC handle), the ranks pass the handles around
+ * by any host channel (torch.distributed in this repository), every rank calls t2d_exchange_connect with all `world`
+ * handles in rank order.  n_local = scenarios per rank (rows are padded to a multiple of 16); slots >= 2 = ring depth.
+ * Every rank must call t2d_exchange_allgather the same number of times, in stream order on each rank. */
 typedef struct t2d_exchange t2d_exchange;
 int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int n_local, int slots, void* ipc_handle_out);
 int t2d_exchange_connect(t2d_exchange* x, const void* handles /* host, world x T2D_IPC_HANDLE_BYTES */);
-int t2d_exchange_attach(t2d_ctx* ctx, t2d_exchange* x /* NULL detaches */);
-/* dst: DEVICE uint8 [world * n_local_rounded]; enqueued on `stream`, bounded wait (a rank that never publishes sets
- * the sticky timed_out word instead of hanging the GPU). */
-int t2d_exchange_gather(t2d_exchange* x, uint8_t* dst, void* stream);
-int t2d_exchange_status(t2d_exchange* x, uint32_t* published, uint32_t* gathered, uint32_t* timed_out);
+/* done_local: DEVICE uint8 [n_local] (t2d_step's `done`); dst: DEVICE uint8 [world * ((n_local + 15) & ~15)], rank order. */
+int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, void* stream);
+int t2d_exchange_status(t2d_exchange* x, uint32_t* steps, uint32_t* timed_out);
 int t2d_exchange_destroy(t2d_exchange* x);
 
 /* Flat batch of `n` independent participants through ONE model (PhysicsModelBase.step):

@@ -60,9 +60,8 @@ SYMBOLS = {
     "t2d_control": (C.c_int, [_P, _P, _P]),
     "t2d_exchange_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "t2d_exchange_connect": (C.c_int, [_P, _P]),
-    "t2d_exchange_attach": (C.c_int, [_P, _P]),
-    "t2d_exchange_gather": (C.c_int, [_P, _P, _P]),
-    "t2d_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "t2d_exchange_allgather": (C.c_int, [_P, _P, _P, _P]),
+    "t2d_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "t2d_exchange_destroy": (C.c_int, [_P]),
     "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 11),
     "t2d_bind_wheel_state": (C.c_int, [_P, _P, _P]),

@@ -81,13 +81,6 @@ struct StepArgs {
   int goal_noact_max;
   long long* dbg_clock;            // optional [n_tiles][8] phase time stamps (T2D_DEBUG_CLOCK); nullptr in production
   float *wheel_f, *wheel_r;        // [N][M] wheel angular speeds of the SingleTrackDrift participants, or nullptr
-  // done-mask exchange over peer memory (t2d_exchange_*): every rank's K1 stores its done bytes straight into every
-  // rank's gather buffer; the last CTA to finish publishes the step on every rank's flag word
-  int xchg_world, xchg_rank, xchg_slots, xchg_first;   // xchg_first: offset of this launch's scenarios in the rank's block
-  int xchg_n_local;
-  unsigned char* xchg_peer[T2D_MAX_RANKS];             // base of every rank's exchange allocation (own included)
-  unsigned* xchg_epoch;                                // local: steps published so far
-  unsigned* xchg_arrive;                               // local: CTAs that finished this launch
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -481,10 +474,6 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
   // ... and wait here, before the first access to the state the previous tick wrote, until that grid has
   // completed and flushed (no-op when the kernel was not launched as a programmatic dependent).
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // step number of this launch for the done exchange: the previous launch (complete by now) left it in xchg_epoch,
-  // and this launch's last CTA bumps it only after every CTA has passed its final barrier
-  const unsigned xchg_step = A.xchg_world ? *reinterpret_cast<volatile unsigned*>(A.xchg_epoch) : 0u;
-
   const int G = A.G, M = A.M;
   const int spw = 32 >> A.g_shift;      // scenarios per warp
   const int sub = lane >> A.g_shift;    // scenario slot inside the warp
@@ -849,12 +838,6 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         if (A.max_step > 0 && cnt > A.max_step) st = T2D_STATUS_TIME_EXCEEDED;  // parking.py:366-369
         if (A.scn_status) A.scn_status[n] = st;
         if (A.done) A.done[n] = st != T2D_STATUS_NORMAL;             // parking.py:243-248
-        if (A.xchg_world) {   // the same byte into slot (step mod slots) of every rank's gather buffer, over NVLink
-          const size_t off = (size_t)(xchg_step % (unsigned)A.xchg_slots) * A.xchg_world * A.xchg_n_local +
-                             (size_t)A.xchg_rank * A.xchg_n_local + A.xchg_first + n;
-          const unsigned char v = st != T2D_STATUS_NORMAL;
-          for (int p = 0; p < A.xchg_world; ++p) A.xchg_peer[p][off] = v;
-        }
       }
     }
     T2D_STAMP(7);
@@ -867,25 +850,6 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     __syncwarp();   // pose tile is reused by the next tile
   }
   if (!staged) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
-  if (A.xchg_world && A.do_physics) {
-    // Publish the step: every CTA fences its peer stores to system scope and counts itself in; the last one
-    // writes (step + 1) into slot `rank` of every rank's flag array with release semantics and opens the next step.
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      const unsigned arrived = atomicAdd(A.xchg_arrive, 1u);
-      if (arrived == gridDim.x - 1) {
-        *A.xchg_arrive = 0u;
-        __threadfence_system();
-        const size_t flag_off = (size_t)A.xchg_slots * A.xchg_world * A.xchg_n_local;   // flags follow the slots (16 B aligned)
-        for (int p = 0; p < A.xchg_world; ++p) {
-          unsigned* f = reinterpret_cast<unsigned*>(A.xchg_peer[p] + flag_off) + A.xchg_rank;
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(xchg_step + 1u) : "memory");
-        }
-        *reinterpret_cast<volatile unsigned*>(A.xchg_epoch) = xchg_step + 1u;
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------- K2
@@ -1153,50 +1117,78 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __
   }
 }
 
-// ============================================================================ done exchange: consumer side
-// One CTA: lanes 0 .. world-1 of warp 0 wait (acquire, system scope) until every rank has published the oldest step
-// this rank has not gathered yet, then the CTA copies that step's slot - all ranks' done masks, in rank order - into
-// dst.  The spin is bounded (about two seconds of SM clocks); on expiry the error word is set and the copy is skipped.
-struct GatherArgs {
-  const unsigned char* base;     // local exchange allocation
-  unsigned* gathered;            // local: steps gathered so far
-  unsigned* error;               // local: sticky time-out flag
-  unsigned char* dst;            // [world * n_local]
-  int world, n_local, slots;
+// ============================================================================ done exchange over peer memory
+// All-gather of the per-rank done masks as ONE small kernel per rank and step, over NVLink / NVSwitch peer memory:
+//   put     every thread stores 16-byte pieces of this rank's mask into slot (step % slots), row `rank`, of EVERY
+//           rank's gather ring (peer stores; the own ring included);
+//   signal  after a CTA barrier, thread 0 fences to system scope and writes step + 1 into word `rank` of every rank's
+//           flag array with release semantics;
+//   wait    threads 0 .. world-1 poll the OWN flag array (acquire, system scope) until every rank has signalled this
+//           step - bounded: ~2 s of SM clocks, then the sticky error word is set and the copy is skipped;
+//   copy    the slot (all ranks' masks in rank order) goes to the caller's array.
+// The kernels of one rank run in stream order and each waits for every rank's signal of the same step, so the ranks'
+// exchange streams advance in lock step and a ring of >= 2 slots is never overwritten before it has been copied out.
+struct AllGatherArgs {
+  unsigned char* peer[T2D_MAX_RANKS];   // every rank's exchange allocation (own included)
+  unsigned char* base;                  // = peer[rank]
+  const unsigned char* local;           // this rank's done mask [n_real]
+  unsigned char* dst;                   // [world * n_local]
+  int world, rank, n_local, n_real, slots;
 };
 
-__global__ void __launch_bounds__(256) t2d_exchange_gather_kernel(const __grid_constant__ GatherArgs A) {
+__global__ void __launch_bounds__(256) t2d_exchange_allgather_kernel(const __grid_constant__ AllGatherArgs A) {
   __shared__ int s_ok;
-  const unsigned want = *A.gathered + 1u;
   const size_t flag_off = (size_t)A.slots * A.world * A.n_local;
+  unsigned* words = reinterpret_cast<unsigned*>(A.base + flag_off);      // [0, MAX_RANKS): flags; then step, -, -, error
+  const unsigned step = words[T2D_MAX_RANKS];
+  const size_t row = (size_t)(step % (unsigned)A.slots) * A.world * A.n_local + (size_t)A.rank * A.n_local;
   if (threadIdx.x == 0) s_ok = 1;
+  // ---- put
+  const int n16 = A.n_local / 16;   // n_local is a multiple of 16; the tail beyond n_real is zero
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+    uint4 v;
+    unsigned char b[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) b[k] = (16 * i + k < A.n_real) ? A.local[16 * i + k] : (unsigned char)0;
+    memcpy(&v, b, 16);
+    for (int p = 0; p < A.world; ++p) reinterpret_cast<uint4*>(A.peer[p] + row)[i] = v;
+  }
   __syncthreads();
+  // ---- signal
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < A.world; ++p) {
+      unsigned* f = reinterpret_cast<unsigned*>(A.peer[p] + flag_off) + A.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(step + 1u) : "memory");
+    }
+  }
+  // ---- wait
   if (threadIdx.x < (unsigned)A.world) {
-    const unsigned* f = reinterpret_cast<const unsigned*>(A.base + flag_off) + threadIdx.x;
+    const unsigned* f = words + threadIdx.x;
     const long long t0 = clock64();
     unsigned v;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v >= want) break;
+      if (v >= step + 1u) break;
       if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }
-      __nanosleep(64);
+      __nanosleep(32);
     }
   }
   __syncthreads();
   if (!s_ok) {
-    if (threadIdx.x == 0) *A.error = 1u;
+    if (threadIdx.x == 0) { words[T2D_MAX_RANKS + 3] = 1u; words[T2D_MAX_RANKS] = step + 1u; }
     return;
   }
+  // ---- copy
   const size_t bytes = (size_t)A.world * A.n_local;
-  const unsigned char* src = A.base + (size_t)((want - 1u) % (unsigned)A.slots) * bytes;
-  if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(A.dst) & 15) == 0) {
+  const unsigned char* src = A.base + (size_t)(step % (unsigned)A.slots) * bytes;
+  if ((reinterpret_cast<uintptr_t>(A.dst) & 15) == 0) {
     for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(A.dst)[i] = reinterpret_cast<const uint4*>(src)[i];
   } else {
     for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) A.dst[i] = src[i];
   }
-  __syncthreads();
-  if (threadIdx.x == 0) *A.gathered = want;
+  if (threadIdx.x == 0) words[T2D_MAX_RANKS] = step + 1u;
 }
 
 // ============================================================================ K5: NPC controllers
@@ -1373,18 +1365,18 @@ static int fail(int code, const std::string& msg) {
 struct t2d_exchange {
   int device = 0, world = 0, rank = 0, n_local = 0, slots = 0;
   size_t bytes = 0;
-  unsigned char* base = nullptr;                 // slots x world x n_local done bytes | world flags | epoch, arrive, gathered, error
+  int n_real = 0;
+  unsigned char* base = nullptr;                 // slots x world x n_local done bytes | MAX_RANKS flag words | step, -, -, error
   unsigned char* peer[T2D_MAX_RANKS] = {};       // every rank's base (own included), valid after t2d_exchange_connect
   bool connected = false;
   size_t flag_off() const { return (size_t)slots * world * n_local; }
-  unsigned* word(int i) const { return reinterpret_cast<unsigned*>(base + flag_off()) + T2D_MAX_RANKS + i; }   // 0 epoch, 1 arrive, 2 gathered, 3 error
+  unsigned* word(int i) const { return reinterpret_cast<unsigned*>(base + flag_off()) + T2D_MAX_RANKS + i; }   // 0 steps done, 3 error
 };
 
 struct t2d_ctx {
   int device = 0, N = 0, M = 0, G = 0, ppl = 4;
   t2d_config cfg{};
   int n_types = 0;
-  t2d_exchange* xchg = nullptr;
   bool has_pointmass = false;
   bool has_drift = false;
   bool kin_only = false;
@@ -1748,15 +1740,6 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
              (!hit_segment || reinterpret_cast<uintptr_t>(hit_segment) % 8 == 0);
   A.vec_ok = vec ? 1 : 0;
 
-  if (c->xchg && do_physics) {
-    const t2d_exchange* x = c->xchg;
-    if (!x->connected) return fail(T2D_E_STATE, "exchange attached but not connected: call t2d_exchange_connect first");
-    if (x->n_local < c->N) return fail(T2D_E_INVALID, "exchange was created for fewer scenarios per rank");
-    if (first != 0 || count != c->N) return fail(T2D_E_UNSUPPORTED, "the done exchange publishes whole ticks: not available through t2d_step_host chunks");
-    A.xchg_world = x->world; A.xchg_rank = x->rank; A.xchg_slots = x->slots; A.xchg_first = first; A.xchg_n_local = x->n_local;
-    for (int p = 0; p < x->world; ++p) A.xchg_peer[p] = x->peer[p];
-    A.xchg_epoch = x->word(0); A.xchg_arrive = x->word(1);
-  }
   A.rb_max = c->rb_max;
   A.dbg_clock = c->dbg_clock;
   A.goal_target = c->goal_target ? c->goal_target + 5 * (size_t)first : nullptr;
@@ -2045,7 +2028,7 @@ int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int
   static_assert(sizeof(cudaIpcMemHandle_t) == T2D_IPC_HANDLE_BYTES, "IPC handle size");
   CUDA_TRY(cudaSetDevice(device));
   t2d_exchange* x = new t2d_exchange();
-  x->device = device; x->world = world; x->rank = rank; x->n_local = (n_local + 15) & ~15; x->slots = slots;
+  x->device = device; x->world = world; x->rank = rank; x->n_real = n_local; x->n_local = (n_local + 15) & ~15; x->slots = slots;
   x->bytes = x->flag_off() + (T2D_MAX_RANKS + 4) * sizeof(unsigned);
   cudaError_t e = cudaMalloc(&x->base, x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
@@ -2077,34 +2060,26 @@ int t2d_exchange_connect(t2d_exchange* x, const void* handles) {
   return T2D_OK;
 }
 
-int t2d_exchange_attach(t2d_ctx* c, t2d_exchange* x) {
-  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
-  if (x && x->device != c->device) return fail(T2D_E_INVALID, "exchange lives on another device");
-  if (x && x->n_local < c->N) return fail(T2D_E_INVALID, "exchange holds fewer scenarios per rank than the context");
-  c->xchg = x;
-  return T2D_OK;
-}
-
-int t2d_exchange_gather(t2d_exchange* x, uint8_t* dst, void* stream) {
-  if (!x || !dst) return fail(T2D_E_INVALID, "exchange / dst is NULL");
-  if (!x->connected) return fail(T2D_E_STATE, "exchange not connected");
+int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, void* stream) {
+  if (!x || !done_local || !dst) return fail(T2D_E_INVALID, "exchange / done_local / dst is NULL");
+  if (!x->connected) return fail(T2D_E_STATE, "exchange not connected: call t2d_exchange_connect first");
   CUDA_TRY(cudaSetDevice(x->device));
-  GatherArgs A{};
-  A.base = x->base; A.gathered = x->word(2); A.error = x->word(3); A.dst = dst;
-  A.world = x->world; A.n_local = x->n_local; A.slots = x->slots;
-  t2d_exchange_gather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(A);
+  AllGatherArgs A{};
+  for (int p = 0; p < x->world; ++p) A.peer[p] = x->peer[p];
+  A.base = x->base; A.local = done_local; A.dst = dst;
+  A.world = x->world; A.rank = x->rank; A.n_local = x->n_local; A.n_real = x->n_real; A.slots = x->slots;
+  t2d_exchange_allgather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;
 }
 
-int t2d_exchange_status(t2d_exchange* x, uint32_t* published, uint32_t* gathered, uint32_t* timed_out) {
+int t2d_exchange_status(t2d_exchange* x, uint32_t* steps, uint32_t* timed_out) {
   if (!x) return fail(T2D_E_INVALID, "exchange is NULL");
   CUDA_TRY(cudaSetDevice(x->device));
   unsigned w[4];
   CUDA_TRY(cudaMemcpy(w, x->word(0), sizeof(w), cudaMemcpyDeviceToHost));
-  if (published) *published = w[0];
-  if (gathered) *gathered = w[2];
+  if (steps) *steps = w[0];
   if (timed_out) *timed_out = w[3];
   return T2D_OK;
 }

@@ -66,16 +66,13 @@ class DoneExchange:
 
 
 class PeerDoneExchange:
-    """The same exchange without a collective call: ``t2d_step`` stores every done byte straight into a gather buffer
-    on every rank (peer stores over NVLink / NVSwitch) and publishes the step on every rank's flag word; ``gather``
-    enqueues one small kernel that waits for all ranks' flags of the oldest ungathered step and copies that step's
-    mask into ``out`` (``t2d_exchange_*`` in ``include/t2d_b200.h``).  Equal shards, one node.
+    """The same exchange without NCCL: one small kernel per rank and step stores the rank's mask into a ring slot on
+    every rank (peer stores over NVLink / NVSwitch), signals the step on every rank's flag word, waits for all ranks'
+    signals and copies the slot out (``t2d_exchange_*`` in ``include/t2d_b200.h``).  Equal shards, one node.
+    ``torch.distributed`` is used once, to pass the CUDA IPC handles around.  Call it like ``DoneExchange``:
+    ``done_all = exchange(out.done)`` on every rank, the same number of times, in stream order."""
 
-    Set-up uses ``torch.distributed`` only to pass the CUDA IPC handles around.  Attach the exchange to every
-    ``BatchedWorld`` that ticks (``attach(world)``); all ranks must tick in the same order.  The gather buffer is a
-    ring of ``slots`` steps: order tick s after this rank's gather of step s - slots // 2 at the latest."""
-
-    def __init__(self, n_local: int, device, slots: int = 8, group=None):
+    def __init__(self, n_local: int, device, slots: int = 4, group=None):
         import ctypes as C
 
         import torch
@@ -94,48 +91,38 @@ class PeerDoneExchange:
         handle = (C.c_ubyte * 64)()
         _lib.check(self.lib.t2d_exchange_create(C.byref(self._x), self.device.index, self.world_size, self.rank, self.n_local,
                                                 self.slots, C.cast(handle, C.c_void_p)))
-        mine = bytes(handle)
         everyone = [None] * self.world_size
-        dist.all_gather_object(everyone, mine, group=group)
+        dist.all_gather_object(everyone, bytes(handle), group=group)
         blob = (C.c_ubyte * (64 * self.world_size)).from_buffer_copy(b"".join(everyone))
         _lib.check(self.lib.t2d_exchange_connect(self._x, C.cast(blob, C.c_void_p)))
-        dist.barrier(group=group)      # every rank has mapped every buffer before anybody ticks
+        dist.barrier(group=group)      # every rank has mapped every buffer before anybody exchanges
         self.out = torch.zeros(self.world_size * self.pad, dtype=torch.uint8, device=self.device)
 
-    def attach(self, world):
-        from . import _lib
-
-        _lib.check(self.lib.t2d_exchange_attach(world._ctx, self._x))
-
-    def detach(self, world):
-        import ctypes as C
-
-        from . import _lib
-
-        _lib.check(self.lib.t2d_exchange_attach(world._ctx, C.c_void_p(0)))
-
-    def gather(self, out=None):
-        """Enqueue the wait-and-copy on the current stream; returns the [world * pad] uint8 tensor (rank order)."""
+    def __call__(self, done_local, out=None):
+        """``done_local``: uint8 [n_local] on this rank -> uint8 [world * pad] (row r = rank r's mask, zero padded);
+        enqueued on the current stream."""
         import ctypes as C
 
         import torch
 
         from . import _lib
 
+        if done_local.numel() != self.n_local or done_local.dtype != torch.uint8 or not done_local.is_contiguous():
+            raise ValueError("done_local must be a contiguous uint8 tensor of this rank's scenarios")
         out = self.out if out is None else out
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(self.lib.t2d_exchange_gather(self._x, C.c_void_p(out.data_ptr()), stream))
+        _lib.check(self.lib.t2d_exchange_allgather(self._x, C.c_void_p(done_local.data_ptr()), C.c_void_p(out.data_ptr()), stream))
         return out
 
     def status(self):
-        """(published, gathered, timed_out) counters of this rank (synchronises the device)."""
+        """(steps exchanged, timed_out) of this rank (synchronises the device)."""
         import ctypes as C
 
         from . import _lib
 
-        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        _lib.check(self.lib.t2d_exchange_status(self._x, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+        a, b = C.c_uint32(), C.c_uint32()
+        _lib.check(self.lib.t2d_exchange_status(self._x, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "_x", None) is not None and self._x.value:

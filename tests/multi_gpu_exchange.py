@@ -1,10 +1,9 @@
 """Two (or more) GPU check of the peer-memory done exchange, launched by torchrun (see test_gpu_exchange.py):
 every rank ticks its own shard; after each tick every rank must hold every rank's done mask, equal to what NCCL's
-all_gather gives, for eager launches and for a CUDA graph of several steps with the gather on a side stream."""
+all_gather gives, for eager launches and for a CUDA graph of several steps with the exchange on a side stream."""
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -20,50 +19,43 @@ def main():
     dev = torch.device("cuda", local)
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=dev)
-    n, m = 200, 24                       # 200 is not a multiple of 16: the gather rows are padded to 208
+    n, m = 200, 24                       # 200 is not a multiple of 16: the gathered rows are padded to 208
     scene = synthetic.config2(n, m, seed=100 + rank, size=60.0)
     w = BatchedWorld(n, m, scene.table, device=dev, max_step=5)
     w.set_map(scene.segments, scene.bounds)
     w.set_state(scene.x, scene.y, scene.heading, scene.speed, type_id=scene.type_id)
-    ex = PeerDoneExchange(n, dev, slots=8)
-    ex.attach(w)
+    ex = PeerDoneExchange(n, dev, slots=2)
     ref = torch.zeros(world * n, dtype=torch.uint8, device=dev)
     seen = 0
-    for t in range(7):                   # eager: tick, gather on the same stream, compare with NCCL
+    for t in range(7):                   # eager: tick, exchange on the same stream, compare with NCCL
         act = torch.from_numpy(synthetic.random_actions(1000 * rank + t, (n, m))).to(dev)
         out = w.step(act)
-        got = ex.gather().clone()
+        got = ex(out.done).clone()
         dist.all_gather_into_tensor(ref, out.done)
         torch.cuda.synchronize()
-        got = got.view(world, ex.pad)[:, :n].reshape(-1)
-        assert torch.equal(got, ref), (rank, t)
+        assert torch.equal(got.view(world, ex.pad)[:, :n].reshape(-1), ref), (rank, t)
+        assert int(got.view(world, ex.pad)[:, n:].sum().item()) == 0
         seen += int(ref.sum().item())
     assert seen > 0
-    # CUDA graph of 6 ticks, gather on a side stream, at most 3 ticks ahead of the own gather
+    # CUDA graph of 6 ticks with the exchange on a side stream (the tick never waits for it)
     side = torch.cuda.Stream(dev)
     outs = [torch.zeros(world * ex.pad, dtype=torch.uint8, device=dev) for _ in range(6)]
     dones = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(6)]
     act = torch.from_numpy(synthetic.random_actions(77 + rank, (n, m))).to(dev)
-    w.reset(torch.ones(n, dtype=torch.uint8, device=dev), {k: getattr(w, k).clone() for k in ("x", "y", "heading", "speed", "vx", "vy")})
     torch.cuda.synchronize()
     dist.barrier()
     g = torch.cuda.CUDAGraph()
     cap = torch.cuda.Stream(dev)
     with torch.cuda.stream(cap):
         with torch.cuda.graph(g, stream=cap):
-            evs = {}
             for i in range(6):
-                if i - 3 in evs:
-                    cap.wait_event(evs[i - 3])
                 out = w.step(act)
                 dones[i].copy_(out.done)
                 e = torch.cuda.Event()
                 e.record(cap)
                 side.wait_event(e)
                 with torch.cuda.stream(side):
-                    ex.gather(outs[i])
-                    evs[i] = torch.cuda.Event()
-                    evs[i].record(side)
+                    ex(dones[i], outs[i])
             cap.wait_stream(side)
     for rep in range(3):
         g.replay()
@@ -72,8 +64,7 @@ def main():
             dist.all_gather_into_tensor(ref, dones[i])
             torch.cuda.synchronize()
             assert torch.equal(outs[i].view(world, ex.pad)[:, :n].reshape(-1), ref), (rank, rep, i)
-    published, gathered, timed_out = ex.status()
-    assert timed_out == 0 and published == gathered == 7 + 18, (published, gathered, timed_out)
+    assert ex.status() == (7 + 18, 0), ex.status()
     dist.barrier()
     if rank == 0:
         print("EXCHANGE_OK", world)
