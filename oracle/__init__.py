@@ -17,15 +17,25 @@ What it is: a float64 restatement of the reference's per-participant algorithm
   from shapely/GEOS (``traffic/event_detection/collision.py``, ``out_bound.py``);
 * ``oracle.scenario``  - the whole tick: physics -> pose -> collisions ->
   out-of-bound -> status priority chain (``envs/parking.py:352-392``);
-* ``oracle/c/``        - the same tick in plain C (gcc), for full-size checks.
+* ``oracle/c/``        - the same tick in plain C (gcc), for full-size checks;
+* ``oracle.lidar``     - ``SingleLineLidar._scan_obstacles`` (``sensor/lidar.py:128-221``);
+* ``oracle.controllers`` - IDM / cruise / adaptive cruise / pure pursuit (``controller/*.py``).
 
 Parity pinning
 --------------
-* Physics: PINNED.  ``oracle/make_golden.py`` imports the *unmodified*
-  reference (``/root/reference/tactics2d/physics``) in the build container and
-  writes ``tests/golden/physics_*.npz``; ``tests/test_oracle_golden.py`` holds
-  the oracle to those vectors (<=1e-12 relative) and to the survey's KATs.
-* Collision / out-of-bound / status: PARITY UNPINNED.  The reference computes
+* Physics (all four models, SingleTrackDrift included): PINNED.
+  ``oracle/make_golden.py`` imports the *unmodified* reference
+  (``/root/reference/tactics2d/physics``) in the build container and writes
+  ``tests/golden/physics_*.npz``; ``tests/test_oracle_golden.py`` holds the
+  oracle to those vectors (<=1e-12 relative) and to the survey's KATs.
+* Controllers and lidar: PINNED to outputs of the unmodified reference classes
+  (``tests/golden/controllers.npz``, ``lidar.npz``).  Those modules import a few
+  shapely containers; the generator supplies stand-ins for exactly the members
+  they touch (``LineString.interpolate``; ring coordinates, ``affine_transform``,
+  ``distance``) and says so - the arithmetic the kernels reproduce is the
+  reference's own code.  ``tests/test_oracle_controllers.py``,
+  ``tests/test_oracle_lidar.py``.
+* Collision / out-of-bound / status / Arrival-NoAction IoU: PARITY UNPINNED.  The reference computes
   these with shapely/GEOS (third-party, ``shapely>=2.0.7,<2.1.0``,
   requirements.txt:18), which is not installable here, and the reference's own
   tests pin no value at that boundary (tests/test_traffic.py is empty,

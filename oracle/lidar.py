@@ -4,9 +4,12 @@
 writes it: obstacle rings -> ego frame (``_rotate_and_filter_obstacles``, :105-126) -> edges -> determinant
 intersection with the beam lines -> the four 1e-8-slack box filters -> min distance, clip, range -> inf.
 
-PARITY UNPINNED by reference tests (tests/test_sensor.py needs data files that are not in the reference tree and
-shapely); the arithmetic below is a line-by-line copy of the NumPy part, the shapely part (``affine_transform``,
-``distance``) is replaced by its definition.  Obstacles are passed as closed rings [K+1, 2] or open polylines [2, 2]
+PINNED to the unmodified reference: ``oracle/make_golden.py`` loads the reference's ``sensor/lidar.py`` by path (with
+stand-ins for the shapely ring container, ``affine_transform`` and ``Map``, the only things it needs from packages that
+are not installable here), runs ``_scan_obstacles`` on 12 scenes x 4 beam / range settings and writes
+``tests/golden/lidar.npz``; ``tests/test_oracle_lidar.py`` holds this restatement to those scans at 1e-12.  (No reference
+test pins a scan: tests/test_sensor.py needs data files that are not in the reference tree.)  The arithmetic below
+restates the NumPy part; the shapely part (``affine_transform``, ``distance``) is replaced by its definition.  Obstacles are passed as closed rings [K+1, 2] or open polylines [2, 2]
 (a map segment); the distance filter of :122-125 only prunes whole obstacles and never changes the scan.
 """
 

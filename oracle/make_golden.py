@@ -151,6 +151,7 @@ def main():
              valid=np.array(vs_out))
     controllers_golden(rng)
     drift_golden(rng)
+    lidar_golden(rng)
     print("golden vectors written to", os.path.normpath(OUT))
 
 
@@ -188,6 +189,120 @@ def drift_golden(rng):
                     rec[i, k] = (s.x, s.y, s.heading, s.speed, wf, wr, a_c, d_c)
             out[f"drift_{name}_{interval}_{delta_t}"] = rec
     np.savez(os.path.join(OUT, "physics_drift.npz"), **out)
+
+
+def lidar_golden(rng):
+    """``SingleLineLidar._scan_obstacles`` (sensor/lidar.py:128-221) of the unmodified reference.
+
+    The module imports ``shapely.affinity.affine_transform``, ``shapely.geometry.{LinearRing, Point, Polygon}`` and
+    ``tactics2d.map.element.Map`` (:11-14), none importable here.  The generator loads ``lidar.py`` / ``sensor_base.py``
+    by path with stand-ins that provide exactly what the scan touches: ring coordinates, ``affine_transform`` of a ring
+    (x' = a x + b y + xoff, y' = d x + e y + yoff - shapely's documented matrix order [a, b, d, e, xoff, yoff]),
+    ``ring.distance(point)`` (only used to skip far obstacles, :122-125) and a ``Map`` with an ``areas`` dict.  The whole
+    ray / edge arithmetic (:160-221) that the kernel reproduces is the reference's own NumPy code."""
+    import importlib.util
+    import types
+
+    class Point:
+        def __init__(self, *a):
+            a = a[0] if len(a) == 1 else a
+            self.x, self.y = float(a[0]), float(a[1])
+
+    class LinearRing:
+        def __init__(self, coords):
+            c = [(float(x), float(y)) for x, y in coords]
+            if c[0] != c[-1]:
+                c.append(c[0])
+            self.coords = c
+
+        def distance(self, pt):
+            c = np.asarray(self.coords)
+            p1, p2 = c[:-1], c[1:]
+            d = p2 - p1
+            dd = (d * d).sum(1)
+            t = np.clip(((np.array([pt.x, pt.y]) - p1) * d).sum(1) / np.where(dd > 0, dd, 1.0), 0, 1)
+            e = p1 + t[:, None] * d - np.array([pt.x, pt.y])
+            return float(np.sqrt((e * e).sum(1)).min())
+
+    class Polygon:
+        def __init__(self, coords):
+            self.exterior = LinearRing(coords)
+
+    def affine_transform(geom, m):
+        a, b, d, e, xo, yo = m
+        return LinearRing([(a * x + b * y + xo, d * x + e * y + yo) for x, y in geom.coords])
+
+    saved = {k: sys.modules.get(k) for k in ("shapely", "shapely.geometry", "shapely.affinity", "tactics2d.map", "tactics2d.map.element")}
+    shp, geo, aff = types.ModuleType("shapely"), types.ModuleType("shapely.geometry"), types.ModuleType("shapely.affinity")
+    geo.Point, geo.LinearRing, geo.Polygon, geo.LineString = Point, LinearRing, Polygon, LinearRing
+    aff.affine_transform = affine_transform
+    shp.geometry, shp.affinity = geo, aff
+    mp, mpe = types.ModuleType("tactics2d.map"), types.ModuleType("tactics2d.map.element")
+
+    class Map:
+        def __init__(self):
+            self.areas = {}
+
+    mpe.Map = Map
+    mp.element = mpe
+    sys.modules.update({"shapely": shp, "shapely.geometry": geo, "shapely.affinity": aff, "tactics2d.map": mp, "tactics2d.map.element": mpe})
+    try:
+        pkg = types.ModuleType("t2d_ref_sensor")
+        pkg.__path__ = [os.path.join(REF, "tactics2d", "sensor")]
+        sys.modules["t2d_ref_sensor"] = pkg
+        for name in ("sensor_base", "lidar"):
+            spec = importlib.util.spec_from_file_location(f"t2d_ref_sensor.{name}", os.path.join(REF, "tactics2d", "sensor", f"{name}.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[f"t2d_ref_sensor.{name}"] = mod
+            spec.loader.exec_module(mod)
+        SingleLineLidar = sys.modules["t2d_ref_sensor.lidar"].SingleLineLidar
+
+        class Area:
+            type_ = "obstacle"
+
+            def __init__(self, ring):
+                self.geometry = LinearRing(ring)
+
+        class Body:
+            def __init__(self, x, y, h, hl, hw):   # Vehicle.get_pose, vehicle.py:133-140,272-281
+                c, s = np.cos(h), np.sin(h)
+                loc = [(hl, -hw), (hl, hw), (-hl, hw), (-hl, -hw)]
+                self.pose = Polygon([(x + cx * c - cy * s, y + cx * s + cy * c) for cx, cy in loc])
+
+            def get_pose(self, frame):
+                return self.pose
+
+        n_scene, n_other = 12, 14
+        f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+        ego = f32(np.stack([rng.uniform(10, 50, n_scene), rng.uniform(10, 50, n_scene), rng.uniform(0, 2 * np.pi, n_scene)], 1))
+        others = f32(np.stack([rng.uniform(0, 60, (n_scene, n_other)), rng.uniform(0, 60, (n_scene, n_other)),
+                               rng.uniform(0, 2 * np.pi, (n_scene, n_other)), rng.uniform(1.5, 3.0, (n_scene, n_other)),
+                               rng.uniform(0.7, 1.1, (n_scene, n_other))], 2))
+        others[:3, 0, :2] = ego[:3, :2] + f32([[0.4, -0.3]])          # a body overlapping the sensor
+        walls = f32([[[0, 0], [60, 0], [60, 1], [0, 1]], [[0, 59], [60, 59], [60, 60], [0, 60]],
+                     [[28, 20], [32, 20], [32, 40], [28, 40]], [[5, 30], [9, 34], [5, 38], [1, 34]]])
+        out = dict(ego=ego, others=others, walls=walls)
+        world = Map()
+        world.areas = {i: Area(w) for i, w in enumerate(walls)}
+        for n_beams, max_range in ((360, 20.0), (500, 12.0), (37, 30.0), (1100, 9.0)):
+            res = np.zeros((n_scene, n_beams))
+            for k in range(n_scene):
+                lid = SingleLineLidar(1, world, perception_range=max_range, freq_scan=1.0, freq_detect=float(n_beams))
+                assert lid.point_density == n_beams
+                lid._position, lid._heading = Point(ego[k, 0], ego[k, 1]), float(ego[k, 2])
+                lid.bind_with(0)
+                bodies = {0: None}
+                bodies.update({j + 1: Body(*others[k, j]) for j in range(n_other)})
+                lid._scan_obstacles(0, bodies, list(bodies))
+                res[k] = lid.scan_result
+            out[f"scan_{n_beams}_{int(max_range)}"] = res
+        np.savez(os.path.join(OUT, "lidar.npz"), **out)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
 
 
 def _shapely_stand_in():
