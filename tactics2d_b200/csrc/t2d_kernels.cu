@@ -980,38 +980,17 @@ __device__ __forceinline__ double point_segment_dist2(double x1, double y1, doub
   return ex * ex + ey * ey;
 }
 
-// Beam window of an edge.  The reference tests every (beam, edge) pair, but its filters (:201-209) keep an
-// intersection only if it lies on the edge (within 1e-8) AND on the beam's forward ray (within 2e-8 of the origin
-// side): a beam can score on an edge only if its direction falls inside the angle the edge subtends at the ego.  The
-// window is that angular interval widened by a whole beam on either side (the 1e-8 slacks are < 1e-5 rad beyond 1 cm
-// from the ego, atan2f is good to 1e-6 rad, beams are >= 1.7e-3 rad apart); edges that come within 1 cm of the ego, or
-// subtend nearly pi, get every beam.  Beams are uniformly spaced, theta_b = 2 pi b / n_beams (lidar.py:160).
-__device__ __forceinline__ int2 beam_window(double x1, double y1, double x2, double y2, double dist2, int n_beams) {
-  if (dist2 < 1e-4) return make_int2(0, n_beams);
-  const float a1 = atan2f((float)y1, (float)x1), a2 = atan2f((float)y2, (float)x2);
-  float diff = a2 - a1;
-  if (diff > 3.14159265f) diff -= 6.28318531f;
-  if (diff < -3.14159265f) diff += 6.28318531f;
-  if (fabsf(diff) > 3.0f) return make_int2(0, n_beams);
-  float start = diff >= 0.0f ? a1 : a2;
-  if (start < 0.0f) start += 6.28318531f;
-  const float inv = (float)n_beams * 0.159154943f;      // beams per radian
-  const int lo = (int)floorf(start * inv) - 1;
-  const int hi = (int)ceilf((start + fabsf(diff)) * inv) + 1;
-  const int cnt = min(hi - lo + 1, n_beams);
-  return make_int2(((lo % n_beams) + n_beams) % n_beams, cnt);
-}
-
+// (beam_window, the per-edge beam interval, lives in t2d_math.cuh so that tests/hostsim can check it on the host.)
 __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __grid_constant__ LidarArgs A) {
   __shared__ double s_edge[LIDAR_WARPS][LIDAR_EDGES][4];
-  __shared__ int2 s_win[LIDAR_WARPS][LIDAR_EDGES];
+  __shared__ BeamWindow s_win[LIDAR_WARPS][LIDAR_EDGES];
   __shared__ float s_best[LIDAR_WARPS][LIDAR_BEAMS];
   __shared__ int s_cnt[LIDAR_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n = (long long)blockIdx.x * LIDAR_WARPS + warp;
   if (n >= A.N) return;
   double(*edge)[4] = s_edge[warp];
-  int2* win = s_win[warp];
+  BeamWindow* win = s_win[warp];
   float* best = s_best[warp];
   int* cnt = &s_cnt[warp];
   const long long base = n * A.M;
@@ -1085,7 +1064,7 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __
       // ---- edge by edge, the lanes share the beams of its window (lidar.py:160-213 for those pairs)
       for (int i = 0; i < n_e; ++i) {
         const double x1 = edge[i][0], y1 = edge[i][1], x2 = edge[i][2], y2 = edge[i][3];
-        const int2 w = win[i];
+        const BeamWindow w = win[i];
         const double d = y2 - y1, e = x1 - x2, f = y1 * x2 - x1 * y2;
         const double xlo = fmin(x1, x2) - 1e-8, xhi = fmax(x1, x2) + 1e-8, ylo = fmin(y1, y2) - 1e-8, yhi = fmax(y1, y2) + 1e-8;
         for (int t = lane; t < w.y; t += 32) {

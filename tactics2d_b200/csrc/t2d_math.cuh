@@ -664,6 +664,34 @@ T2D_HD void pointmass_euler_step(OneIO& io, const Params& p, int n_steps, double
   sincos_fast(io.h, &io.sh, &io.ch);
 }
 
+// ------------------------------------------------------------------------------------------
+// Lidar (K4)
+// ------------------------------------------------------------------------------------------
+struct BeamWindow { int x, y; };   // first beam, number of beams (wraps modulo n_beams)
+
+// Beam window of an edge.  The reference tests every (beam, edge) pair, but its filters (:201-209) keep an
+// intersection only if it lies on the edge (within 1e-8) AND on the beam's forward ray (within 2e-8 of the origin
+// side): a beam can score on an edge only if its direction falls inside the angle the edge subtends at the ego.  The
+// window is that angular interval widened by a whole beam on either side (the 1e-8 slacks are < 1e-5 rad beyond 1 cm
+// from the ego, atan2f is good to 1e-6 rad, beams are >= 1.7e-3 rad apart); edges that come within 1 cm of the ego, or
+// subtend nearly pi, get every beam.  Beams are uniformly spaced, theta_b = 2 pi b / n_beams (lidar.py:160).
+T2D_HD BeamWindow beam_window(double x1, double y1, double x2, double y2, double dist2, int n_beams) {
+  if (dist2 < 1e-4) return BeamWindow{0, n_beams};
+  const float a1 = atan2f((float)y1, (float)x1), a2 = atan2f((float)y2, (float)x2);
+  float diff = a2 - a1;
+  if (diff > 3.14159265f) diff -= 6.28318531f;
+  if (diff < -3.14159265f) diff += 6.28318531f;
+  if (fabsf(diff) > 3.0f) return BeamWindow{0, n_beams};
+  float start = diff >= 0.0f ? a1 : a2;
+  if (start < 0.0f) start += 6.28318531f;
+  const float inv = (float)n_beams * 0.159154943f;      // beams per radian
+  const int lo = (int)floorf(start * inv) - 1;
+  const int hi = (int)ceilf((start + fabsf(diff)) * inv) + 1;
+  const int cnt = hi - lo + 1 < n_beams ? hi - lo + 1 : n_beams;
+  return BeamWindow{((lo % n_beams) + n_beams) % n_beams, cnt};
+}
+
+
 // ==========================================================================================
 // Closed-set predicates.  *_f32 return 1 (intersects), 0 (disjoint) or -1 (inside the fp32
 // error bound: caller must ask the *_f64 twin).  *_f64 evaluate exactly the float64 formulas

@@ -113,6 +113,14 @@ void hs_drift(int n, const AbiParams* ap, int n_steps, double dt, double dt_rem,
   }
 }
 
+// lidar beam windows: edges (x1, y1, x2, y2) in the ego frame, distance^2 of the edge to the origin -> (first, count)
+void hs_beam_window(int n, const double* edge, const double* dist2, int n_beams, int32_t* out) {
+  for (int i = 0; i < n; ++i) {
+    const BeamWindow w = beam_window(edge[4 * i], edge[4 * i + 1], edge[4 * i + 2], edge[4 * i + 3], dist2[i], n_beams);
+    out[2 * i] = w.x; out[2 * i + 1] = w.y;
+  }
+}
+
 float hs_wrap(float phi) { return wrap_two_pi(phi); }
 
 // rows: x, y, heading, l, w (fp32, as the kernel sees them)

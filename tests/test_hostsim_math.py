@@ -319,3 +319,48 @@ def test_drift_vs_reference_golden(hostsim, name, interval, delta_t):
     w0 = want[:, 0, :6].astype(np.float32).astype(np.float64)
     got, app = run(*w0.T, g["actions2"])
     check(got, app, oracle(w0, g["actions2"]))
+
+
+@pytest.mark.parametrize("n_beams", [37, 360, 1100, 3600])
+def test_lidar_beam_window_is_conservative(hostsim, n_beams):
+    """Every beam that survives the reference's own filters (sensor/lidar.py:188-213) on an edge lies inside the beam window
+    the kernel computes for that edge (so culling the other beams cannot change a scan); windows are also small on average."""
+    rng = np.random.default_rng(n_beams)
+    n = 6000
+    R = 20.0
+    c = rng.uniform(-R, R, (n, 2))
+    half = rng.uniform(0.01, 6.0, n)[:, None] * np.stack([np.cos(a := rng.uniform(0, 2 * np.pi, n)), np.sin(a)], 1)
+    e = np.concatenate([c - half, c + half], 1)
+    e[:300, :2] = rng.uniform(-0.02, 0.02, (300, 2))            # edges starting at / next to the sensor
+    e[300:600] = np.concatenate([-half[300:600] * 3, half[300:600] * 3], 1) + rng.uniform(-1e-3, 1e-3, (300, 4))   # through the origin
+    e[600:900, 1] = 0.0
+    e[600:900, 3] = 0.0                                         # on the x axis (the beam-0 / wrap-around direction)
+    e[900:1200, 0] = e[900:1200, 2]                             # vertical edges
+    x1, y1, x2, y2 = e.T
+    dx, dy = x2 - x1, y2 - y1
+    dd = dx * dx + dy * dy
+    t = np.clip(-(x1 * dx + y1 * dy) / np.where(dd > 0, dd, 1.0), 0, 1)
+    dist2 = (x1 + t * dx) ** 2 + (y1 + t * dy) ** 2
+    out = np.zeros((n, 2), np.int32)
+    hostsim.hs_beam_window(C.c_int(n), _p(np.ascontiguousarray(e)), _p(np.ascontiguousarray(dist2)), C.c_int(n_beams), _p(out))
+    # the reference's per-pair arithmetic, one edge at a time
+    theta = np.linspace(0, 2 * np.pi, n_beams, endpoint=False)
+    a, b = np.sin(theta), -np.cos(theta)
+    lx, ly = np.cos(theta) * R, np.sin(theta) * R
+    tz = 1e-8
+    total = 0
+    for i in range(n):
+        d, ee, f = y2[i] - y1[i], x1[i] - x2[i], y1[i] * x2[i] - x1[i] * y2[i]
+        det = a * ee - b * d
+        par = det == 0
+        det = np.where(par, 1.0, det)
+        rx, ry = (b * f) / det, (-a * f) / det
+        ok = ~par
+        ok &= ~(rx > np.maximum(tz, lx) + tz) & ~(rx < np.minimum(-tz, lx) - tz) & ~(ry > np.maximum(tz, ly) + tz) & ~(ry < np.minimum(-tz, ly) - tz)
+        ok &= ~(rx > max(x1[i], x2[i]) + tz) & ~(rx < min(x1[i], x2[i]) - tz) & ~(ry > max(y1[i], y2[i]) + tz) & ~(ry < min(y1[i], y2[i]) - tz)
+        first, cnt = out[i]
+        assert 0 <= first < n_beams and 1 <= cnt <= n_beams
+        inside = ((np.arange(n_beams) - first) % n_beams) < cnt
+        assert not np.any(ok & ~inside), (i, e[i], np.nonzero(ok & ~inside)[0][:5], first, cnt)
+        total += cnt
+    assert total / n < 0.45 * n_beams + 8     # (this sample is dominated by long edges close to the sensor)
