@@ -255,7 +255,13 @@ def run_ours(args):
     if world_size > 1 and args.exchange == "peer":
         from tactics2d_b200.distributed import PeerDoneExchange
 
-        peer = PeerDoneExchange(n, device, slots=4)
+        try:
+            peer = PeerDoneExchange(n, device, slots=4)
+        except RuntimeError as e:   # every rank raises together (the set-up is agreed on collectively): use NCCL instead
+            peer = None
+            args.exchange = "nccl"
+            if rank == 0:
+                print(f"[bench] {e}; falling back to --exchange nccl", file=sys.stderr)
 
     def restore():
         for w, p in zip(worlds, pools):

@@ -72,7 +72,7 @@ class PeerDoneExchange:
     ``torch.distributed`` is used once, to pass the CUDA IPC handles around.  Call it like ``DoneExchange``:
     ``done_all = exchange(out.done)`` on every rank, the same number of times, in stream order."""
 
-    def __init__(self, n_local: int, device, slots: int = 4, group=None):
+    def __init__(self, n_local: int, device, slots: int = 4, group=None, lib=None):
         import ctypes as C
 
         import torch
@@ -80,7 +80,7 @@ class PeerDoneExchange:
 
         from . import _lib
 
-        self.lib = _lib.load()
+        self.lib = lib if lib is not None else _lib.load()
         self.device = torch.device(device)
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -89,13 +89,29 @@ class PeerDoneExchange:
         self.slots = int(slots)
         self._x = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        _lib.check(self.lib.t2d_exchange_create(C.byref(self._x), self.device.index, self.world_size, self.rank, self.n_local,
-                                                self.slots, C.cast(handle, C.c_void_p)))
+        # Every step of the set-up is agreed on by all ranks before anybody proceeds: a rank whose CUDA IPC call fails
+        # (no peer access, a container without shared IPC namespaces) must not leave the others waiting in a collective.
+        problem = None
+        try:
+            _lib.check(self.lib.t2d_exchange_create(C.byref(self._x), self.device.index or 0, self.world_size, self.rank, self.n_local,
+                                                    self.slots, C.cast(handle, C.c_void_p)))
+        except Exception as e:   # noqa: BLE001 - reported to every rank below
+            problem = f"create: {e}"
         everyone = [None] * self.world_size
-        dist.all_gather_object(everyone, bytes(handle), group=group)
-        blob = (C.c_ubyte * (64 * self.world_size)).from_buffer_copy(b"".join(everyone))
-        _lib.check(self.lib.t2d_exchange_connect(self._x, C.cast(blob, C.c_void_p)))
-        dist.barrier(group=group)      # every rank has mapped every buffer before anybody exchanges
+        dist.all_gather_object(everyone, (problem, bytes(handle)), group=group)
+        if all(p is None for p, _ in everyone):
+            blob = (C.c_ubyte * (64 * self.world_size)).from_buffer_copy(b"".join(h for _, h in everyone))
+            try:
+                _lib.check(self.lib.t2d_exchange_connect(self._x, C.cast(blob, C.c_void_p)))
+            except Exception as e:   # noqa: BLE001
+                problem = f"connect: {e}"
+        verdicts = [None] * self.world_size
+        dist.all_gather_object(verdicts, problem if problem is not None else everyone[self.rank][0], group=group)
+        failed = {r: v for r, v in enumerate(verdicts) if v is not None}
+        failed.update({r: p for r, (p, _) in enumerate(everyone) if p is not None})
+        if failed:
+            self.close()
+            raise RuntimeError(f"peer-memory done exchange unavailable (rank -> reason): {failed}")
         self.out = torch.zeros(self.world_size * self.pad, dtype=torch.uint8, device=self.device)
 
     def __call__(self, done_local, out=None):

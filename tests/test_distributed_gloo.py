@@ -81,3 +81,76 @@ def test_done_mask_all_gather_world2(n_total):
     for rank, got, got2, local, (lo, hi) in results:
         assert np.array_equal(got, done_all) and np.array_equal(got2, done_all)
         assert np.array_equal(local, done_all[lo:hi])
+
+
+class _FakeExchangeLib:
+    """Stands in for libt2d_b200's t2d_exchange_* entry points (no GPU in this suite): records calls, can fail on demand."""
+
+    def __init__(self, rank, fail_connect_on=None, fail_create_on=None):
+        self.rank, self.fail_connect_on, self.fail_create_on = rank, fail_connect_on, fail_create_on
+        self.connected_with = None
+        self.destroyed = False
+
+    def t2d_exchange_create(self, xref, device, world, rank, n_local, slots, handle):
+        import ctypes as C
+
+        if self.fail_create_on == rank:
+            return -2
+        xref._obj.value = 4242
+        C.memmove(handle.value, bytes([rank]) * 64, 64)
+        return 0
+
+    def t2d_exchange_connect(self, x, blob):
+        import ctypes as C
+
+        if self.fail_connect_on == self.rank:
+            return -2
+        self.connected_with = C.string_at(blob.value, 128)
+        return 0
+
+    def t2d_exchange_destroy(self, x):
+        self.destroyed = True
+        return 0
+
+
+def _exchange_setup_worker(rank, world, port, mode, q):
+    import torch
+    import torch.distributed as dist
+
+    from tactics2d_b200.distributed import PeerDoneExchange
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = _FakeExchangeLib(rank, fail_connect_on=1 if mode == "connect" else None, fail_create_on=0 if mode == "create" else None)
+        try:
+            ex = PeerDoneExchange(100, torch.device("cpu"), slots=2, lib=lib)
+            q.put((rank, "ok", lib.connected_with == bytes([0]) * 64 + bytes([1]) * 64, ex.pad, tuple(ex.out.shape)))
+        except RuntimeError as e:
+            q.put((rank, "raised", str(e), lib.destroyed, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["ok", "connect", "create"])
+def test_peer_exchange_setup_is_agreed_on_by_all_ranks(mode):
+    """The CUDA IPC set-up of PeerDoneExchange either succeeds on every rank or raises on every rank - a rank whose
+    create / connect fails never leaves the others waiting in a collective (bench.py then falls back to NCCL)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_setup_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if mode == "ok":
+        assert [r[1:] for r in results] == [("ok", True, 112, (224,))] * 2      # handles in rank order, rows padded to 16
+    else:
+        assert all(r[1] == "raised" and "unavailable" in r[2] for r in results)
+        bad = 1 if mode == "connect" else 0
+        assert all(f"{bad}:" in r[2] for r in results)
