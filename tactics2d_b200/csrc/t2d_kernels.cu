@@ -3,8 +3,12 @@
 // K1  t2d_step_kernel      fused physics -> pose -> dynamic collision (broadphase + filtered
 //                          narrowphase) -> static collision against the map tile in shared
 //                          memory (uniform-grid broadphase) -> out-of-bound -> status chain.
+//                          (+ t2d_drift_kernel: pre-pass for SingleTrackDrift participants.)
 // K2  t2d_reset_kernel     masked re-initialisation from a pool of initial states.
 // K3  t2d_physics_kernel   flat batch through one physics model (PhysicsModelBase.step).
+// K4  t2d_lidar_kernel     single-line lidar of every scenario's ego (per-edge beam windows).
+// K5  t2d_control_kernel   NPC controllers: IDM, cruise / adaptive cruise, pure pursuit.
+//     t2d_exchange_allgather_kernel   all-gather of the done masks over NVLink peer memory.
 //
 // Work decomposition of K1: a scenario (M <= 128 participants) is owned by a group of G lanes of
 // one warp, 4 consecutive participants per lane (one float4 per state array per lane: coalesced
@@ -30,10 +34,9 @@
 
 namespace t2d {
 
-constexpr int MAX_PPL = 4;              // participants per lane: 1, 2 or 4 (template parameter of K1)
 constexpr int MAX_WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host picks 2, 4 or 8 warps per CTA
-constexpr int POSE_PER_WARP = 128;      // 32 lanes x MAX_PPL
+constexpr int POSE_PER_WARP = 128;      // 32 lanes x 4 participants per lane (PPL, template parameter of K1: 2 or 4)
 constexpr int MAP_SMEM_LIMIT = 120 * 1024;
 
 struct MapHeader {   // 64 bytes, start of the map blob
