@@ -27,7 +27,7 @@ class Trajectory:
         self.stable_freq = stable_freq
         self._states = {}
         self._frames: List[int] = []
-        self._current = None
+        self._current_state = None
 
     def __len__(self):
         return len(self._frames)
@@ -58,7 +58,7 @@ class Trajectory:
 
     @property
     def current_state(self):
-        return self._current
+        return self._current_state
 
     @property
     def average_speed(self):
@@ -70,7 +70,7 @@ class Trajectory:
 
     def get_state(self, frame: int = None) -> State:
         if frame is None:
-            return self._current
+            return self._current_state
         if frame not in self._states:
             raise KeyError(f"Time stamp {frame} is not found in the trajectory {self.id_}.")
         return self._states[frame]
@@ -84,7 +84,7 @@ class Trajectory:
         if state.frame in self._states:
             logging.warning(f"State at time stamp {state.frame} is already in trajectory {self.id_}. It will be overwritten.")
             self._states[state.frame] = state
-            self._current = state
+            self._current_state = state
             return
         if len(self._frames) > 1 and self.stable_freq:
             if state.frame - self._frames[-1] != self._frames[-1] - self._frames[-2]:
@@ -92,7 +92,7 @@ class Trajectory:
                 logging.warning(f"The time interval of the trajectory {self.id_} is uneven.")
         self._frames.append(state.frame)
         self._states[state.frame] = state
-        self._current = state
+        self._current_state = state
 
     append_state = add_state
 
@@ -107,7 +107,7 @@ class Trajectory:
         if state is None:
             first = self.initial_state
             if keep_history:
-                self._current = first
+                self._current_state = first
                 return
             state = first
         self._states.clear()
