@@ -188,7 +188,15 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
   // term instead of an accumulated sum.
   float c[W], s[W], w1[W], Sx[W], Sy[W], Sv[W], kdt[W], adt[W], vlo[W], vhi[W], k[W], a[W];
   bool small = true;
-  bool lin = n_steps >= 2;   // no participant of this group touches a speed bound during the tick (see the fast loop)
+#if defined(T2D_NO_FAST_KIN)   // (measurement builds only: always take the general loop)
+  bool lin = false;
+#else
+  // fast loop: no participant of this group touches a speed bound during the tick, and the tick has at most 24
+  // sub-steps - the carried rotation accumulates rounding quadratically in the sub-step count (measured against float64
+  // at v <= 69 m/s: 4e-6 at 20 sub-steps, 9e-6 at 100, 2e-5 at 40 sub-steps of a 200 ms tick; the general loop stays
+  // below 7e-6 there), so longer ticks keep the general loop
+  bool lin = n_steps >= 2 && n_steps <= 24;
+#endif
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     a[i] = clampf(io.acc[i], p[i]->accel_lo, p[i]->accel_hi);       // :192

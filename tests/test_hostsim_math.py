@@ -364,3 +364,22 @@ def test_lidar_beam_window_is_conservative(hostsim, n_beams):
         assert not np.any(ok & ~inside), (i, e[i], np.nonzero(ok & ~inside)[0][:5], first, cnt)
         total += cnt
     assert total / n < 0.45 * n_beams + 8     # (this sample is dominated by long edges close to the sensor)
+
+
+@pytest.mark.parametrize("interval,delta_t", [(100, 5), (100, 2), (100, 1), (200, 5), (50, 3)])
+def test_kinematics_error_budget_near_the_origin(hostsim, interval, delta_t):
+    """The 1e-5 contract as an ABSOLUTE bound (|x|, |y| <= 1, where the relative scale is 1) over the full speed range of the
+    medium car, for short and long sub-step counts: the carried-rotation fast loop (<= 24 sub-steps) and the general loop."""
+    rng = np.random.default_rng(interval * 10 + delta_t)
+    n = 50000
+    p = TypeParams(**MEDIUM, **RNG)
+    table = TypeTable([p])
+    t = table.as_oracle_table()
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    x, y, h = f32(rng.uniform(-1, 1, n)), f32(rng.uniform(-1, 1, n)), f32(rng.uniform(0, 2 * np.pi, n))
+    v, act = f32(rng.uniform(-16, 69, n)), f32(np.stack([rng.uniform(-12, 6, n), rng.uniform(-0.8, 0.8, n)], 1))
+    (x1, y1, h1, v1, _, _), _ = run_physics(hostsim, table, np.zeros(n), x, y, h, v, 0 * x, 0 * x, act, interval, delta_t)
+    o = P.step_kinematics(x, y, h, v, act[:, 0], act[:, 1], t["lf"][0], t["lr"][0], (t["steer_lo"][0], t["steer_hi"][0]),
+                          (t["speed_lo"][0], t["speed_hi"][0]), (t["accel_lo"][0], t["accel_hi"][0]), interval, delta_t)
+    assert rel_err(x1, o["x"]).max() < 1e-5 and rel_err(y1, o["y"]).max() < 1e-5
+    assert heading_err(h1, o["heading"]).max() < 5e-6 and rel_err(v1, o["speed"]).max() < 1e-6
