@@ -1384,6 +1384,7 @@ struct t2d_ctx {
   float goal_threshold = 0.95f;
   int goal_noact_max = 0;
   bool use_pdl = true;             // T2D_PDL=0 disables programmatic dependent launch
+  int grid_limit = 0;              // T2D_GRID_LIMIT=k: at most k CTAs of the persistent tick grid per SM (experiments; 0 = occupancy)
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
   int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1444,6 +1445,7 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   }
   c->ppl = ppl;
   if (const char* e = getenv("T2D_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("T2D_GRID_LIMIT")) c->grid_limit = std::max(0, atoi(e));
   if (const char* e = getenv("T2D_HOST_CHUNKS")) c->host_chunks = std::max(0, std::min(atoi(e), (int)t2d_ctx::MAX_HOST_CHUNKS));
   int g = 1;
   while (g * ppl < m_participants) g <<= 1;
@@ -1787,7 +1789,9 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
     c->occ_val[wpc] = per_sm < 1 ? 1 : per_sm;
     c->occ_smem[wpc] = smem;
   }
-  const long long resident = (long long)c->sm_count * c->occ_val[wpc];
+  int per_sm_ctas = c->occ_val[wpc];
+  if (c->grid_limit > 0) per_sm_ctas = std::min(per_sm_ctas, c->grid_limit);   // T2D_GRID_LIMIT: leave CTA slots to other streams
+  const long long resident = (long long)c->sm_count * per_sm_ctas;
   const int grid = (int)std::max(1LL, std::min(ctas_needed, resident));
   {
     cudaLaunchConfig_t cfg{};
@@ -2050,7 +2054,12 @@ int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* 
   for (int p = 0; p < x->world; ++p) A.peer[p] = x->peer[p];
   A.base = x->base; A.local = done_local; A.dst = dst;
   A.world = x->world; A.rank = x->rank; A.n_local = x->n_local; A.n_real = x->n_real; A.slots = x->slots;
-  t2d_exchange_allgather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(A);
+  int threads = 256;
+  if (const char* e = getenv("T2D_EXCHANGE_THREADS")) {   // experiments: a smaller CTA finds a home on a busy SM sooner
+    const int v = atoi(e);
+    if (v >= 32 && v <= 256 && v % 32 == 0 && v >= x->world) threads = v;
+  }
+  t2d_exchange_allgather_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;
