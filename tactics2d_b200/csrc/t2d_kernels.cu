@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -178,12 +179,6 @@ __device__ __forceinline__ bool seg_hit(const Pose& a, const float4 sg) {
 
 __device__ __noinline__ bool oob_exact(const Pose a, float xmin, float xmax, float ymin, float ymax) {
   return out_of_bound_f64(a.x, a.y, a.h, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax);
-}
-
-// Single-participant kinematics for mixed-model tiles (one out-of-line copy instead of PPL inlined ones).
-__device__ __noinline__ void kin1_step(KinIO<1>& io, const Params& p, int n_steps, float dt, float dt_rem) {
-  const Params* const p1[1] = {&p};
-  kinematics_step<1>(io, p1, n_steps, dt, dt_rem);
 }
 
 // Every model except the fp32 kinematic fast path (one copy of the fp64 code per kernel).  SingleTrackDrift is NOT
@@ -547,12 +542,17 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         }
       }
     } else {
-      for (int i = 0; i < nvalid; ++i) {
-        sx[i] = A.x[idx0 + i]; sy[i] = A.y[idx0 + i]; shd[i] = A.h[idx0 + i]; sv[i] = A.v[idx0 + i];
-        tidv[i] = A.type_id[idx0 + i];
-        if (A.do_physics) {
-          a0[i] = A.action[2 * (idx0 + i)]; a1[i] = A.action[2 * (idx0 + i) + 1];
-          if (A.needs_vel_in) { svx[i] = A.vx[idx0 + i]; svy[i] = A.vy[idx0 + i]; }
+      // ragged / unaligned rows: predicated scalar loads, fully unrolled (a runtime-indexed loop would demote every
+      // per-participant array of this kernel to local memory)
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        if (i < nvalid) {
+          sx[i] = A.x[idx0 + i]; sy[i] = A.y[idx0 + i]; shd[i] = A.h[idx0 + i]; sv[i] = A.v[idx0 + i];
+          tidv[i] = A.type_id[idx0 + i];
+          if (A.do_physics) {
+            a0[i] = A.action[2 * (idx0 + i)]; a1[i] = A.action[2 * (idx0 + i) + 1];
+            if (A.needs_vel_in) { svx[i] = A.vx[idx0 + i]; svy[i] = A.vy[idx0 + i]; }
+          }
         }
       }
     }
@@ -571,51 +571,56 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     T2D_STAMP(1);
     // ------------------------------------------------------------------ physics
     float ch[PPL], sh[PPL];
-    bool active[PPL];
+    bool active[PPL], kin[PPL];
     const Params* pp[PPL];
-    bool all_kin = true;
+    bool lane_all_kin = true, lane_any_kin = false;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
       active[i] = tidv[i] < A.n_types;
       pp[i] = &s_table[active[i] ? tidv[i] : 0];
-      all_kin = all_kin && active[i] && (pp[i]->model == MODEL_KINEMATICS);
+      kin[i] = active[i] && (pp[i]->model == MODEL_KINEMATICS);
+      lane_all_kin = lane_all_kin && kin[i];
+      lane_any_kin = lane_any_kin || kin[i];
+      ch[i] = 1.0f; sh[i] = 0.0f;
     }
     if (A.do_physics) {
-      if (__all_sync(0xffffffffu, all_kin)) {
+      // Kinematic participants of the whole warp advance together in the packed 4-chain loop; slots holding another
+      // model (or nothing) ride along on a neutral row (zero speed / action, unbounded ranges) and are discarded.
+      if (__any_sync(0xffffffffu, lane_any_kin)) {
+        const Params* const null_row = &s_table[A.n_types];
+        const Params* pk[PPL];
         KinIO<PPL> io;
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          io.x[i] = sx[i]; io.y[i] = sy[i]; io.h[i] = shd[i]; io.v[i] = sv[i];
-          io.acc[i] = a0[i]; io.steer[i] = a1[i];
+          pk[i] = kin[i] ? pp[i] : null_row;
+          io.x[i] = kin[i] ? sx[i] : 0.0f; io.y[i] = kin[i] ? sy[i] : 0.0f;
+          io.h[i] = kin[i] ? shd[i] : 0.0f; io.v[i] = kin[i] ? sv[i] : 0.0f;
+          io.acc[i] = kin[i] ? a0[i] : 0.0f; io.steer[i] = kin[i] ? a1[i] : 0.0f;
         }
-        kinematics_step<PPL>(io, pp, A.n_steps, A.dt, A.dt_rem);
+        kinematics_step<PPL>(io, pk, A.n_steps, A.dt, A.dt_rem);
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          sx[i] = io.x[i]; sy[i] = io.y[i]; shd[i] = io.h[i]; sv[i] = io.v[i];
-          svx[i] = io.vx[i]; svy[i] = io.vy[i]; ch[i] = io.ch[i]; sh[i] = io.sh[i];
+          if (kin[i]) {
+            sx[i] = io.x[i]; sy[i] = io.y[i]; shd[i] = io.h[i]; sv[i] = io.v[i];
+            svx[i] = io.vx[i]; svy[i] = io.vy[i]; ch[i] = io.ch[i]; sh[i] = io.sh[i];
+          }
         }
-      } else {
+      }
+      if (!lane_all_kin) {
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          if (!active[i]) {
-            ch[i] = 1.0f; sh[i] = 0.0f;
-          } else if (pp[i]->model == MODEL_KINEMATICS) {
-            KinIO<1> io;
-            io.x[0] = sx[i]; io.y[0] = sy[i]; io.h[0] = shd[i]; io.v[0] = sv[i];
-            io.acc[0] = a0[i]; io.steer[0] = a1[i];
-            kin1_step(io, *pp[i], A.n_steps, A.dt, A.dt_rem);
-            sx[i] = io.x[0]; sy[i] = io.y[0]; shd[i] = io.h[0]; sv[i] = io.v[0];
-            svx[i] = io.vx[0]; svy[i] = io.vy[0]; ch[i] = io.ch[0]; sh[i] = io.sh[0];
-          } else if constexpr (!KIN_ONLY) {
-            OneIO io;
-            io.x = sx[i]; io.y = sy[i]; io.h = shd[i]; io.v = sv[i]; io.vx = svx[i]; io.vy = svy[i];
-            io.a0 = a0[i]; io.a1 = a1[i];
-            io.ch = 1.0f; io.sh = 0.0f;
-            other_model_step(io, *pp[i], A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
-            sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
-            ch[i] = io.ch; sh[i] = io.sh;
-          } else {
-            sincos_fast(shd[i], &sh[i], &ch[i]);   // static participant: the pose only
+          if (active[i] && !kin[i]) {
+            if constexpr (!KIN_ONLY) {
+              OneIO io;
+              io.x = sx[i]; io.y = sy[i]; io.h = shd[i]; io.v = sv[i]; io.vx = svx[i]; io.vy = svy[i];
+              io.a0 = a0[i]; io.a1 = a1[i];
+              io.ch = 1.0f; io.sh = 0.0f;
+              other_model_step(io, *pp[i], A.n_steps, A.dt_d, A.dt_rem_d, A.interval_d);
+              sx[i] = io.x; sy[i] = io.y; shd[i] = io.h; sv[i] = io.v; svx[i] = io.vx; svy[i] = io.vy;
+              ch[i] = io.ch; sh[i] = io.sh;
+            } else {
+              sincos_fast(shd[i], &sh[i], &ch[i]);   // static participant: the pose only
+            }
           }
         }
       }
@@ -631,10 +636,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         st_vec<float, PPL>(A.vx + idx0, svx);
         st_vec<float, PPL>(A.vy + idx0, svy);
       } else {
-        for (int i = 0; i < nvalid; ++i) {
-          if (!active[i]) continue;
-          A.x[idx0 + i] = sx[i]; A.y[idx0 + i] = sy[i]; A.h[idx0 + i] = shd[i]; A.v[idx0 + i] = sv[i];
-          A.vx[idx0 + i] = svx[i]; A.vy[idx0 + i] = svy[i];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          if (i < nvalid && active[i]) {
+            A.x[idx0 + i] = sx[i]; A.y[idx0 + i] = sy[i]; A.h[idx0 + i] = shd[i]; A.v[idx0 + i] = sv[i];
+            A.vx[idx0 + i] = svx[i]; A.vy[idx0 + i] = svy[i];
+          }
         }
       }
     } else {
@@ -806,10 +813,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
       if (A.hit_index) st_vec<int16_t, PPL>(A.hit_index + idx0, h16);
       if (A.hit_segment) st_vec<int16_t, PPL>(A.hit_segment + idx0, s16);
     } else {
-      for (int i = 0; i < nvalid; ++i) {
-        if (A.flags) A.flags[idx0 + i] = fl[i];
-        if (A.hit_index) A.hit_index[idx0 + i] = (int16_t)hit[i];
-        if (A.hit_segment) A.hit_segment[idx0 + i] = (int16_t)hseg[i];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        if (i < nvalid) {
+          if (A.flags) A.flags[idx0 + i] = fl[i];
+          if (A.hit_index) A.hit_index[idx0 + i] = (int16_t)hit[i];
+          if (A.hit_segment) A.hit_segment[idx0 + i] = (int16_t)hseg[i];
+        }
       }
     }
 
@@ -1333,6 +1343,8 @@ using namespace t2d;
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static std::mutex g_smem_mutex;
+static int g_smem_configured[64][4];   // [device][kernel variant]: dynamic shared memory opted in so far (process-wide)
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -1348,6 +1360,7 @@ struct t2d_exchange {
   int device = 0, world = 0, rank = 0, n_local = 0, slots = 0;
   size_t bytes = 0;
   int n_real = 0;
+  int threads = 256;                             // CTA size of the exchange kernel (T2D_EXCHANGE_THREADS, read once at create)
   unsigned char* base = nullptr;                 // slots x world x n_local done bytes | MAX_RANKS flag words | step, -, -, error
   unsigned char* peer[T2D_MAX_RANKS] = {};       // every rank's base (own included), valid after t2d_exchange_connect
   bool connected = false;
@@ -1375,7 +1388,6 @@ struct t2d_ctx {
   int32_t* step_count = nullptr;
   int sm_count = 148;
   int max_smem_optin = 0;
-  int configured_smem = -1;
   float rb_max = 0.0f;
   const float* goal_target = nullptr;
   float* goal_iou = nullptr;
@@ -1384,6 +1396,7 @@ struct t2d_ctx {
   float goal_threshold = 0.95f;
   int goal_noact_max = 0;
   bool use_pdl = true;             // T2D_PDL=0 disables programmatic dependent launch
+  int wpc_override = 0;            // T2D_WPC=w: warps per CTA of the tick (experiments; 0 = pick from the batch size)
   int grid_limit = 0;              // T2D_GRID_LIMIT=k: at most k CTAs of the persistent tick grid per SM (experiments; 0 = occupancy)
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
@@ -1446,6 +1459,10 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   c->ppl = ppl;
   if (const char* e = getenv("T2D_PDL")) c->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("T2D_GRID_LIMIT")) c->grid_limit = std::max(0, atoi(e));
+  if (const char* e = getenv("T2D_WPC")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= MAX_WARPS_PER_CTA) c->wpc_override = v;
+  }
   if (const char* e = getenv("T2D_HOST_CHUNKS")) c->host_chunks = std::max(0, std::min(atoi(e), (int)t2d_ctx::MAX_HOST_CHUNKS));
   int g = 1;
   while (g * ppl < m_participants) g <<= 1;
@@ -1513,15 +1530,25 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
     if (p.model == T2D_MODEL_POINTMASS_NEWTON || p.model == T2D_MODEL_POINTMASS_EULER) c->has_pointmass = true;
   }
   CUDA_TRY(cudaSetDevice(c->device));
-  if (!c->d_table) CUDA_TRY(cudaMalloc(&c->d_table, T2D_MAX_TYPES * sizeof(Params)));
+  if (!c->d_table) CUDA_TRY(cudaMalloc(&c->d_table, (T2D_MAX_TYPES + 1) * sizeof(Params)));
   {
-    std::vector<Params> rows(n_types);
+    std::vector<Params> rows(n_types + 1);
     for (int i = 0; i < n_types; ++i) {
       AbiParams a;
       memcpy(&a, &table[i], sizeof(AbiParams));
       rows[i] = derive_params(a);
     }
-    CUDA_TRY(cudaMemcpy(c->d_table, rows.data(), n_types * sizeof(Params), cudaMemcpyHostToDevice));
+    {
+      // row n_types: the neutral kinematic row that K1's packed loop gives to slots holding another model or nothing
+      // (zero speed and action in, unbounded ranges: every product stays finite and the result is discarded)
+      AbiParams a{};
+      a.lf = 1.0f; a.lr = 1.0f;
+      a.steer_lo = a.speed_lo = a.accel_lo = -INFINITY;
+      a.steer_hi = a.speed_hi = a.accel_hi = INFINITY;
+      a.model = MODEL_KINEMATICS; a.shape = SHAPE_NONE;
+      rows[n_types] = derive_params(a);
+    }
+    CUDA_TRY(cudaMemcpy(c->d_table, rows.data(), (n_types + 1) * sizeof(Params), cudaMemcpyHostToDevice));
   }
   c->n_types = n_types;
   c->has_drift = has_drift;
@@ -1529,7 +1556,6 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   c->kin_only = true;
   for (int i = 0; i < n_types; ++i)
     if (table[i].model != T2D_MODEL_KINEMATICS && table[i].model != T2D_MODEL_STATIC) c->kin_only = false;
-  c->configured_smem = -1;
   for (int w = 0; w < 9; ++w) c->occ_smem[w] = -1;
   return T2D_OK;
 }
@@ -1730,7 +1756,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.goal_iou = c->goal_iou ? c->goal_iou + first : nullptr;
   A.goal_last_pose = c->goal_last_pose ? c->goal_last_pose + 4 * (size_t)first : nullptr;
   A.goal_noact_count = c->goal_noact_count ? c->goal_noact_count + first : nullptr; A.goal_threshold = c->goal_threshold; A.goal_noact_max = c->goal_noact_max;
-  const int table_bytes = ((c->n_types * (int)sizeof(Params) + 15) / 16) * 16;
+  const int table_bytes = (((c->n_types + 1) * (int)sizeof(Params) + 15) / 16) * 16;   // + the neutral row
   const int spw = 32 / c->G;
   const long long tiles = ((long long)count + spw - 1) / spw;
   // warps per CTA: the largest of 8 / 4 / 2 that still leaves >= 6 CTAs per SM (small batches balance
@@ -1739,10 +1765,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   for (int w : {8, 4}) {
     if ((tiles + w - 1) / w >= 6LL * c->sm_count) { wpc = w; break; }
   }
-  if (const char* e = getenv("T2D_WPC")) {   // experiments
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
-  }
+  if (c->wpc_override > 0) wpc = c->wpc_override;   // T2D_WPC (experiments), read once at t2d_create
   {
     int off = (A.map_in_smem ? A.map_bytes : 0) + table_bytes;
     A.off_poseA = off; off += wpc * POSE_PER_WARP * (int)sizeof(float4);
@@ -1771,9 +1794,16 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
     kern = c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, true> : (kernel_t)t2d_step_kernel<4, true>;
   else
     kern = c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, false> : (kernel_t)t2d_step_kernel<4, false>;
-  if (smem > c->configured_smem) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    c->configured_smem = smem;
+  {
+    // cudaFuncSetAttribute applies to the kernel function for the whole process and SETS the value: worlds of
+    // different sizes share it, so the opt-in is tracked per (device, kernel variant) and only ever raised.
+    const int variant = (c->kin_only ? 2 : 0) + (c->ppl == 2 ? 1 : 0);
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    int& configured = g_smem_configured[c->device % 64][variant];
+    if (smem > configured) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = smem;
+    }
   }
   if (do_physics && c->has_drift) {
     const long long total = (long long)count * c->M;
@@ -2015,6 +2045,10 @@ int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int
   CUDA_TRY(cudaSetDevice(device));
   t2d_exchange* x = new t2d_exchange();
   x->device = device; x->world = world; x->rank = rank; x->n_real = n_local; x->n_local = (n_local + 15) & ~15; x->slots = slots;
+  if (const char* e = getenv("T2D_EXCHANGE_THREADS")) {   // experiments: a smaller CTA finds a home on a busy SM sooner
+    const int v = atoi(e);
+    if (v >= 32 && v <= 256 && v % 32 == 0 && v >= world) x->threads = v;
+  }
   x->bytes = x->flag_off() + (T2D_MAX_RANKS + 4) * sizeof(unsigned);
   cudaError_t e = cudaMalloc(&x->base, x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
@@ -2054,11 +2088,7 @@ int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* 
   for (int p = 0; p < x->world; ++p) A.peer[p] = x->peer[p];
   A.base = x->base; A.local = done_local; A.dst = dst;
   A.world = x->world; A.rank = x->rank; A.n_local = x->n_local; A.n_real = x->n_real; A.slots = x->slots;
-  int threads = 256;
-  if (const char* e = getenv("T2D_EXCHANGE_THREADS")) {   // experiments: a smaller CTA finds a home on a busy SM sooner
-    const int v = atoi(e);
-    if (v >= 32 && v <= 256 && v % 32 == 0 && v >= x->world) threads = v;
-  }
+  const int threads = x->threads;
   t2d_exchange_allgather_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());

@@ -98,29 +98,54 @@ T2D_HD float wrap_two_pi(float phi) {
 // sincos without the library's large-argument (Payne-Hanek) path inlined at every call site: Cody-Waite
 // reduction to [-pi/4, pi/4] (three-term pi/2, exact for |x| <= 512) + degree-7/8 polynomials; abs error < 1e-7.
 // Larger arguments go to one out-of-line copy of the library routine.
+// (The slow path returns its results BY VALUE: handing it the callers' output pointers would force both results of
+//  every inlined sincos_fast through local memory, also on the fast path.)
+struct SinCos { float s, c; };
 #if defined(__CUDACC__)
-__host__ __device__ __noinline__ void sincosf_slow(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+__host__ __device__ __noinline__ SinCos sincosf_slow(float x) { SinCos r; sincosf(x, &r.s, &r.c); return r; }
 #else
-inline void sincosf_slow(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+inline SinCos sincosf_slow(float x) { SinCos r; sincosf(x, &r.s, &r.c); return r; }
 #endif
 
-T2D_HD void sincos_fast(float x, float* sn, float* cs) {
-  if (!(fabsf(x) <= 512.0f)) {
-    sincosf_slow(x, sn, cs);
-    return;
-  }
-  const float k = rintf(x * 0.636619772f);
-  float r = fmaf(-k, 1.570556640625f, x);
-  r = fmaf(-k, 2.396702766418457e-4f, r);
-  r = fmaf(-k, 1.5893254712295857e-8f, r);
+// The two polynomials on the reduced argument r in [-pi/4, pi/4].
+T2D_HD void sincos_poly(float r, float& s, float& c) {
   const float z = r * r;
-  const float s = fmaf(r * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
-  const float c = fmaf(z * z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
-                       fmaf(-0.5f, z, 1.0f));
-  const int q = (int)k;
-  const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
-  *sn = (q & 2) ? -a : a;
-  *cs = ((q + 1) & 2) ? -b : b;
+  s = fmaf(r * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+  c = fmaf(z * z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+           fmaf(-0.5f, z, 1.0f));
+}
+
+T2D_HD void sincos_fast(float x, float* sn, float* cs) {
+  float so, co;
+  if (!(fabsf(x) <= 512.0f)) {
+    const SinCos r = sincosf_slow(x);
+    so = r.s; co = r.c;
+  } else {
+    const float k = rintf(x * 0.636619772f);
+    float r = fmaf(-k, 1.570556640625f, x);
+    r = fmaf(-k, 2.396702766418457e-4f, r);
+    r = fmaf(-k, 1.5893254712295857e-8f, r);
+    float s, c;
+    sincos_poly(r, s, c);
+    const int q = (int)k;
+    const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    so = (q & 2) ? -a : a;
+    co = ((q + 1) & 2) ? -b : b;
+  }
+  *sn = so;
+  *cs = co;
+}
+
+// sincos of an angle that is almost always inside [-pi/4, pi/4] (a clipped steering angle): there the reduction of
+// sincos_fast is the identity (k = 0), so the polynomials alone give bit-identical results.
+T2D_HD void sincos_narrow(float x, float* sn, float* cs) {
+  if (fabsf(x) <= 0.78f) {
+    float s, c;
+    sincos_poly(x, s, c);
+    *sn = s; *cs = c;
+  } else {
+    sincos_fast(x, sn, cs);
+  }
 }
 
 // Small-angle rotation, |d| <= 0.25 (Taylor: |err| < 2e-9 on cos, 1.3e-8 relative on sin).
@@ -204,7 +229,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     io.acc[i] = a[i];
     io.steer[i] = d;
     float sd, cd;
-    sincos_fast(d, &sd, &cd);
+    sincos_narrow(d, &sd, &cd);
     float tan_d = sd / cd;
     float tb = p[i]->lr_over_L * tan_d;       // tan(beta), beta = atan(lr/L tan delta)  :127  (L = lf + lr, :85)
     float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
