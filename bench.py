@@ -256,7 +256,7 @@ def run_ours(args):
         from tactics2d_b200.distributed import PeerDoneExchange
 
         try:
-            peer = PeerDoneExchange(n, device, slots=4)
+            peer = PeerDoneExchange(n, device, lag=args.lag)
         except RuntimeError as e:   # every rank raises together (the set-up is agreed on collectively): use NCCL instead
             peer = None
             args.exchange = "nccl"
@@ -302,6 +302,33 @@ def run_ours(args):
         one_step(i)
     join_comm()
     barrier()
+
+    # self-check of the exchange, every run: the masks our peer-memory kernel delivers (call k -> step k - lag) must
+    # equal NCCL's all_gather of the same masks
+    exchange_check = None
+    if peer is not None:
+        history, ok, checked = [], True, 0
+        ref = torch.zeros(world_size * n, dtype=torch.uint8, device=device)
+        for t in range(args.lag + 4):
+            out = worlds[t % R].step(actions[t % R])
+            got = peer(out.done, done_all).clone()
+            dist.all_gather_into_tensor(ref, out.done)
+            torch.cuda.synchronize()
+            history.append(ref.clone())
+            k = peer.calls - 1 - args.lag        # the step this call delivered (counted over all calls so far)
+            h = len(history) - 1 - args.lag      # ... as an index into this loop's history
+            if h >= 0:
+                ok = ok and bool(torch.equal(got.view(world_size, peer.pad)[:, :n].reshape(-1), history[h]))
+                checked += 1
+        flag = torch.tensor([1 if ok else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_check = {"ok": bool(flag.item()), "steps_compared": checked, "against": "all_gather_into_tensor (NCCL)"}
+        if not exchange_check["ok"]:
+            if rank == 0:
+                print("[bench] peer-memory done exchange disagrees with NCCL all_gather", file=sys.stderr)
+            os._exit(4)
+        restore()
+        barrier()
 
     # capture the K-step timed region in a CUDA graph ----------------------------------------------
     graph = None
@@ -435,8 +462,9 @@ def run_ours(args):
                        "timed_region": "CUDA graph of K steps" if graph is not None else "eager launch loop of K steps",
                        "reps": len(reps_ms), "rep_ms_min": min(reps_ms), "rep_ms_max": max(reps_ms),
                        "collective": ("none (1 GPU)" if world_size == 1 else
-                                      "all-gather(done) per step by our own peer-memory kernel (t2d_exchange_allgather: put, signal, wait, copy), side stream, overlaps the next tick" if peer is not None else
-                                      "all_gather(done) per step (NCCL, side stream, overlaps the next tick)")},
+                                      f"all-gather(done) per step by our own peer-memory kernel (t2d_exchange_allgather_lagged: put + signal per peer, wait, copy; lag {args.lag}: call k delivers the masks of step k - {args.lag}), side stream, overlaps the next tick" if peer is not None else
+                                      "all_gather(done) per step (NCCL, side stream, overlaps the next tick)"),
+                       "exchange_selfcheck": exchange_check},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "t2d_step_kernel",
@@ -483,6 +511,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer", help="N > 1: how the done masks are exchanged")
+    ap.add_argument("--lag", type=int, default=2, help="peer exchange: deliver the gathered masks this many steps late (0 = synchronous)")
     ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

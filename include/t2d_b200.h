@@ -189,11 +189,17 @@ int t2d_check_events(t2d_ctx* ctx, uint8_t* flags, int16_t* hit_index, int16_t* 
 int t2d_set_goal(t2d_ctx* ctx, const float* target, float arrival_threshold, int no_action_max_step, float* iou_out,
                  float* last_pose, int32_t* no_action_count);
 
-/* Masked re-initialisation: for every scenario n with mask[n] != 0 copy row pool_index[n] of the
- * [P, M] pool arrays into the bound state and zero step_count[n]. pool_type may be NULL. */
+/* Masked re-initialisation (ScenarioManager.reset, envs/parking.py:397-441; ParticipantBase.reset): for every scenario n
+ * with mask[n] != 0 copy row pool_index[n] (row n when pool_index is NULL) of the [n_pool, M] pool arrays into the bound
+ * state and zero step_count[n]; pool_vx / pool_vy may be NULL (then speed x (cos, sin)(heading)).  Everything else the
+ * world owns per participant starts fresh too: the NoAction detector state of t2d_set_goal, the controllers' last_accel
+ * (0), and the SingleTrackDrift wheel speeds bound with t2d_bind_wheel_state - from the pool columns of
+ * t2d_bind_reset_wheel_pool when bound, else free rolling (speed / wheel_radius). */
 int t2d_reset(t2d_ctx* ctx, const uint8_t* mask, const int32_t* pool_index, int n_pool, const float* pool_x,
               const float* pool_y, const float* pool_heading, const float* pool_speed, const float* pool_vx,
               const float* pool_vy, void* stream);
+/* Optional initial wheel speeds for t2d_reset: DEVICE arrays [n_pool][M] indexed like the other pool columns (NULL, NULL unbinds). */
+int t2d_bind_reset_wheel_pool(t2d_ctx* ctx, const float* pool_omega_front, const float* pool_omega_rear);
 
 /* Single-line lidar of the ego (participant 0) of every scenario: SingleLineLidar._scan_obstacles
  * (tactics2d/sensor/lidar.py:128-221).  n_beams = point_density (lidar.py:49), max_range = perception range;
@@ -243,6 +249,29 @@ int t2d_set_paths(t2d_ctx* ctx, const float* xy, const int32_t* offsets, int n_p
  * t2d_step.  action: DEVICE [N, M, 2] fp32. */
 int t2d_control(t2d_ctx* ctx, float* action, void* stream);
 
+/* ---- the env layer: ego action, host-resident ego caller, reward / terminated / truncated ------------------------------
+ * ParkingEnv.step takes ONE action, the ego's (steering, accel) (envs/parking.py:219-239); the other participants of a
+ * batched scenario are driven on the device (t2d_control) or by the rows of the caller's action array.
+ * t2d_set_ego_action binds a DEVICE array [N][2] (or NULL to unbind): while bound, t2d_control and t2d_step take the
+ * action of participant 0 of every scenario from it (t2d_control also writes it into row 0 of `action`). */
+int t2d_set_ego_action(t2d_ctx* ctx, const float* ego_action /* device [N][2], 8-byte aligned */);
+/* One tick for a caller whose policy lives on the host and drives only the ego: copies ego_action_host [N][2] to the
+ * device (8 N bytes instead of the 8 N M of t2d_step_host), runs t2d_control when controllers are set (the other
+ * participants' rows of `action`, a DEVICE array [N][M][2] owned by the caller, never leave the device), the tick, and
+ * copies status + done back ([N] each, HOST); synchronises `stream` before returning. */
+int t2d_step_host_ego(t2d_ctx* ctx, const float* ego_action_host, float* action, uint8_t* flags, int16_t* hit_index,
+                      int16_t* hit_segment, uint8_t* scn_status_host, uint8_t* done_host, void* stream);
+/* What ParkingEnv.step computes after check_status (envs/parking.py:240-256, _get_reward :148-190), for all scenarios in
+ * one launch, from the tick's outputs `flags` [N][M] and `scn_status` [N]: traffic_status [N][M] (TrafficStatus codes,
+ * status.py:52-61; may be NULL), terminated / truncated / done [N] (may be NULL), reward [N] by the reference's chain
+ * (-5 collision, -1 time exceeded / no action, -5 out of bound, +5 completed, else time penalty + IoU gain + 0.1 x
+ * progress towards the target).  max_iou / min_dist [N]: the per-episode extrema the reward keeps (ParkingEnv._max_iou,
+ * _min_dist_to_target; initialise to -inf / +inf; NULL when no goal is set); with reset_trackers_on_done they are
+ * re-initialised for the scenarios that are done, so that `done` can go straight into t2d_reset.  All arrays DEVICE. */
+int t2d_env_epilogue(t2d_ctx* ctx, const uint8_t* flags, const uint8_t* scn_status, float* reward, uint8_t* terminated,
+                     uint8_t* truncated, uint8_t* traffic_status, uint8_t* done, float* max_iou, float* min_dist,
+                     int reset_trackers_on_done, void* stream);
+
 /* ---- done-mask exchange across the GPUs of one node, over peer memory (NVLink / NVSwitch) -------------------------
  * Scenarios are sharded across ranks (one process per GPU); the one exchange of the path is "every rank learns every
  * rank's done mask of this tick" - the terminated / truncated vector a central learner or reset scheduler reads
@@ -260,6 +289,13 @@ int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int
 int t2d_exchange_connect(t2d_exchange* x, const void* handles /* host, world x T2D_IPC_HANDLE_BYTES */);
 /* done_local: DEVICE uint8 [n_local] (t2d_step's `done`); dst: DEVICE uint8 [world * ((n_local + 15) & ~15)], rank order. */
 int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, void* stream);
+/* The same exchange taken off the critical path: the call posts this step's mask (put + signal, nothing to wait for)
+ * and delivers into dst the gathered masks of the step `lag` calls earlier, whose signals have long arrived (the first
+ * `lag` calls deliver nothing and leave dst untouched).  The consumer of the gathered masks - a central learner or
+ * reset scheduler - is behind the simulation anyway; the ticks of the ranks no longer meet once per step.
+ * Needs slots >= 2 * lag + 2.  lag = 0 is t2d_exchange_allgather.  If a rank fails to signal within the time-out
+ * (T2D_EXCHANGE_TIMEOUT_MS, default ~2 s) dst is filled with 0xFF and the sticky timed_out word is set. */
+int t2d_exchange_allgather_lagged(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, int lag, void* stream);
 int t2d_exchange_status(t2d_exchange* x, uint32_t* steps, uint32_t* timed_out);
 int t2d_exchange_destroy(t2d_exchange* x);
 

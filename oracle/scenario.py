@@ -233,3 +233,51 @@ def status_with_goal(flags, type_id, step_count_new, arrived, noact, max_step=0,
         st = np.where(step_count_new > max_step, TIME_EXCEEDED, st)   # :366-369
     st = st.astype(np.uint8)
     return st, (st != NORMAL).astype(np.uint8)
+
+
+def env_epilogue(flags, scn_status, step_count, max_step, iou=None, ego_xy=None, target=None, max_iou=None, min_dist=None,
+                 reset_trackers=True):
+    """``ParkingEnv.step`` after ``check_status`` (envs/parking.py:240-256) with ``_get_reward`` (:148-190), per scenario, in
+    float64.  ``flags`` [N, M] event bytes, ``scn_status`` [N]; with a goal: ``iou`` [N], ``ego_xy`` [N, 2], ``target``
+    [N, 5] and the per-episode extrema ``max_iou`` / ``min_dist`` [N] (updated copies are returned).
+    Returns dict(reward, terminated, truncated, done, traffic_status, max_iou, min_dist)."""
+    flags = np.asarray(flags)
+    N = flags.shape[0]
+    traffic = np.where(flags & F_STATIC, 3, np.where(flags & F_DYNAMIC, 4, 1)).astype(np.uint8)   # status.py:52-61
+    reward = np.zeros(N, np.float64)
+    term = np.zeros(N, bool)
+    trunc = np.zeros(N, bool)
+    max_iou = None if max_iou is None else np.array(max_iou, np.float64)
+    min_dist = None if min_dist is None else np.array(min_dist, np.float64)
+    for n in range(N):
+        st = int(scn_status[n])
+        ego_ts = int(traffic[n, 0]) if st == FAILED else 1      # check_status returns at the first detector that fires
+        term[n] = st == COMPLETED                                # :243-244
+        trunc[n] = (not term[n]) and (st != NORMAL or ego_ts != 1)   # :245-248
+        if ego_ts in (3, 4):
+            r = -5.0                                             # :151-152
+        elif st in (TIME_EXCEEDED, NO_ACTION):
+            r = -1.0                                             # :153-157
+        elif st == OUT_BOUND:
+            r = -5.0                                             # :158-159
+        elif st == COMPLETED:
+            r = 5.0                                              # :160-161
+        else:
+            r = -np.tanh(float(step_count[n]) / max_step) * 0.001 if max_step and max_step > 0 else 0.0   # :163
+            if iou is not None and max_iou is not None:
+                r += float(iou[n]) if max_iou[n] == -np.inf else float(iou[n]) - max_iou[n]   # :164-169
+                max_iou[n] = max(max_iou[n], float(iou[n]))                                   # :170
+            if target is not None and min_dist is not None:
+                d = float(np.hypot(ego_xy[n, 0] - target[n, 0], ego_xy[n, 1] - target[n, 1]))   # :172-185
+                if d < min_dist[n]:
+                    if np.isfinite(min_dist[n]):
+                        r += (min_dist[n] - d) * 0.1             # :186-187
+                    min_dist[n] = d                              # :188
+        reward[n] = r
+        if reset_trackers and (term[n] or trunc[n]):
+            if max_iou is not None:
+                max_iou[n] = -np.inf
+            if min_dist is not None:
+                min_dist[n] = np.inf
+    return dict(reward=reward, terminated=term, truncated=trunc, done=(term | trunc).astype(np.uint8), traffic_status=traffic,
+                max_iou=max_iou, min_dist=min_dist)

@@ -17,12 +17,14 @@ w.set_map(sc.segments, sc.bounds)
 w.set_state(sc.x, sc.y, sc.heading, sc.speed, type_id=sc.type_id)
 act = torch.from_numpy(synthetic.random_actions(3, (n, m))).to(dev)
 done_all = torch.zeros(world * (n + 16), dtype=torch.uint8, device=dev)
-ex = PeerDoneExchange(n, dev, slots=4)
+exs = {lag: PeerDoneExchange(n, dev, lag=lag) for lag in (0, 1, 2)}
+ex = exs[0]
 side = torch.cuda.Stream(dev)
 
 
 def build(mode):
     use_side = mode.endswith("_side")
+    px = exs[int(mode[4])] if mode.startswith("peer") else None   # "peerL_same" / "peerL_side": lag L
 
     def body(cap):
         for i in range(K):
@@ -33,7 +35,7 @@ def build(mode):
                 e = torch.cuda.Event(); e.record(cap); side.wait_event(e)
             with torch.cuda.stream(side if use_side else cap):
                 if mode.startswith("peer"):
-                    ex(out.done, done_all[: world * ex.pad])
+                    px(out.done, done_all[: world * px.pad])
                 else:
                     dist.all_gather_into_tensor(done_all[: world * n], out.done)
         if use_side:
@@ -65,7 +67,9 @@ def timed(g, reps=20):
 
 res = {}
 for name, mode in (("tick only", "none"), ("tick + NCCL all_gather, same stream", "nccl_same"), ("tick + NCCL all_gather, side stream", "nccl_side"),
-                   ("tick + peer-memory all-gather kernel, same stream", "peer_same"), ("tick + peer-memory all-gather kernel, side stream", "peer_side")):
+                   ("tick + peer-memory all-gather kernel, same stream", "peer0_same"), ("tick + peer-memory all-gather kernel, side stream", "peer0_side"),
+                   ("tick + peer kernel, lag 1, same stream", "peer1_same"), ("tick + peer kernel, lag 1, side stream", "peer1_side"),
+                   ("tick + peer kernel, lag 2, same stream", "peer2_same"), ("tick + peer kernel, lag 2, side stream", "peer2_side")):
     try:
         res[name] = timed(build(mode))
     except Exception as e:   # keep going: the other rows are still informative
@@ -75,5 +79,5 @@ for name, mode in (("tick only", "none"), ("tick + NCCL all_gather, same stream"
 if rank == 0:
     for k, v in res.items():
         print("%-52s %7.2f us / step" % (k, v))
-    print("exchange status (steps, timed_out):", ex.status())
+    print("exchange status (steps, timed_out) per lag:", {lag: x.status() for lag, x in exs.items()})
 sys.stdout.flush(); dist.barrier(); os._exit(0)

@@ -52,6 +52,9 @@ SYMBOLS = {
     "t2d_step": (C.c_int, [_P] + [_P] * 7),
     "t2d_step_host": (C.c_int, [_P] + [_P] * 7),
     "t2d_check_events": (C.c_int, [_P] + [_P] * 4),
+    "t2d_set_ego_action": (C.c_int, [_P, _P]),
+    "t2d_step_host_ego": (C.c_int, [_P] + [_P] * 8),
+    "t2d_env_epilogue": (C.c_int, [_P] + [_P] * 9 + [C.c_int, _P]),
     "t2d_set_goal": (C.c_int, [_P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "t2d_reset": (C.c_int, [_P, _P, _P, C.c_int] + [_P] * 7),
     "t2d_lidar_scan": (C.c_int, [_P, C.c_int, C.c_float, _P, _P, _P]),
@@ -61,10 +64,12 @@ SYMBOLS = {
     "t2d_exchange_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "t2d_exchange_connect": (C.c_int, [_P, _P]),
     "t2d_exchange_allgather": (C.c_int, [_P, _P, _P, _P]),
+    "t2d_exchange_allgather_lagged": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "t2d_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "t2d_exchange_destroy": (C.c_int, [_P]),
     "t2d_physics_step": (C.c_int, [C.c_int, C.POINTER(TypeParamsC), C.c_int, C.c_int, C.c_int] + [_P] * 11),
     "t2d_bind_wheel_state": (C.c_int, [_P, _P, _P]),
+    "t2d_bind_reset_wheel_pool": (C.c_int, [_P, _P, _P]),
     "t2d_debug_set_clock_buffer": (C.c_int, [_P, _P]),
     "t2d_launch_count": (C.c_int64, []),
 }

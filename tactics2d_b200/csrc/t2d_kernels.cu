@@ -35,8 +35,11 @@
 
 namespace t2d {
 
-constexpr int MAX_WARPS_PER_CTA = 8;
-constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host picks 2, 4 or 8 warps per CTA
+#ifndef T2D_K1_MAX_WARPS
+#define T2D_K1_MAX_WARPS 8
+#endif
+constexpr int MAX_WARPS_PER_CTA = T2D_K1_MAX_WARPS;
+constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host picks the warps per CTA (pick_wpc)
 constexpr int POSE_PER_WARP = 128;      // 32 lanes x 4 participants per lane (PPL, template parameter of K1: 2 or 4)
 constexpr int MAP_SMEM_LIMIT = 120 * 1024;
 
@@ -56,6 +59,7 @@ struct StepArgs {
   const uint8_t* type_id;
   int32_t* step_count;
   const float* action;
+  const float* ego_action;         // [N][2] action of participant 0 of every scenario (overrides its row of `action`), or nullptr
   uint8_t* flags;
   int16_t* hit_index;
   int16_t* hit_segment;
@@ -256,6 +260,51 @@ __device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, const fl
   }
 }
 
+// One word of the partner loop = IPW iterations x PPL own participants x 2 partners.  X / Y: the partner positions of
+// the word's iterations (two per float2); nx2 / ny2: the lane's own positions, negated; nthr2: minus the squared
+// broadphase reach.  The margin of a pair, d^2 - thr, is <= 0 for a candidate; a NaN position (empty slot) gives a NaN
+// margin, which neither the minimum nor the comparison picks up.  FIRST: word 0, where the combinations with partner
+// offset <= 0 (the lane's own participants and pairs owned by the other end) are left out at compile time.
+template <int PPL, bool FIRST>
+__device__ __forceinline__ float pair_word_min(const float2 (&X)[16 / PPL], const float2 (&Y)[16 / PPL], const float2 (&nx2)[PPL],
+                                               const float2 (&ny2)[PPL], const float2 (&nthr2)[PPL]) {
+  float m = INFINITY;
+#pragma unroll
+  for (int uu = 0; uu < 16 / PPL; ++uu) {
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const bool v0 = !FIRST || (2 * uu - i >= 1), v1 = !FIRST || (2 * uu + 1 - i >= 1);
+      if (!v0 && !v1) continue;
+      const float2 dx = __fadd2_rn(X[uu], nx2[i]), dy = __fadd2_rn(Y[uu], ny2[i]);
+      const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2[i]));
+      if (v0 && v1) m = fminf(m, fminf(d2.x, d2.y));
+      else if (v0) m = fminf(m, d2.x);
+      else m = fminf(m, d2.y);
+    }
+  }
+  return m;
+}
+
+// The verdict bits of a word whose minimum margin was <= 0: bit ((uu * PPL + i) * 2 + e), the same margins recomputed.
+template <int PPL, bool FIRST>
+__device__ __forceinline__ unsigned pair_word_bits(const float2 (&X)[16 / PPL], const float2 (&Y)[16 / PPL], const float2 (&nx2)[PPL],
+                                                   const float2 (&ny2)[PPL], const float2 (&nthr2)[PPL]) {
+  unsigned bits = 0;
+#pragma unroll
+  for (int uu = 0; uu < 16 / PPL; ++uu) {
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const bool v0 = !FIRST || (2 * uu - i >= 1), v1 = !FIRST || (2 * uu + 1 - i >= 1);
+      if (!v0 && !v1) continue;
+      const float2 dx = __fadd2_rn(X[uu], nx2[i]), dy = __fadd2_rn(Y[uu], ny2[i]);
+      const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2[i]));
+      if (v0 && d2.x <= 0.0f) bits |= 1u << ((uu * PPL + i) * 2);
+      if (v1 && d2.y <= 0.0f) bits |= 2u << ((uu * PPL + i) * 2);
+    }
+  }
+  return bits;
+}
+
 // Broadphase slow path.  `bits` holds the distance-test verdicts of four partner-loop iterations of this lane:
 // bit ((uu * PPL + i) * 2 + e) = own participant m0 + i against extended slot m0 + 2 (u_base + uu) + e.  Keep the
 // combinations whose partner offset q is 1..Mh (every unordered pair once; q <= 0 are the lane's own participants
@@ -430,8 +479,13 @@ __device__ __noinline__ unsigned ego_goal_events(const StepArgs& A, long long n,
 // ---------------------------------------------------------------------------- K1
 // KIN_ONLY: every type in the table is SingleTrackKinematics or static - the fp64 models are compiled out
 // (their register footprint would otherwise bound the occupancy of the whole kernel).
+#if defined(T2D_K1_MAXNREG)   // experiments: an explicit register budget instead of the launch bounds
+#define T2D_K1_BOUNDS __maxnreg__(T2D_K1_MAXNREG)
+#else
+#define T2D_K1_BOUNDS __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3))
+#endif
 template <int PPL, bool KIN_ONLY>
-__global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kernel(const __grid_constant__ StepArgs A) {
+__global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   // carve: [map blob | 16B aligned] [type table] [pose tiles, hit mins, queues, positions] [mbarrier]; every
   // offset, shift and count that depends only on the launch shape comes precomputed from the host
@@ -451,7 +505,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + A.off_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if defined(T2D_DEBUG_CLOCK)
   const long long t_entry = A.dbg_clock ? clock64() : 0;
+#endif
   // Programmatic dependent launch: let the next tick's grid start launching now (its prologue - shared-memory
   // carve, mbarrier, TMA staging of the static table / map - overlaps this grid's tail) ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -501,9 +557,15 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     if (nvalid < 0) nvalid = 0;
     const long long idx0 = n * M + m0;
 
+#if defined(T2D_DEBUG_CLOCK)   // phase time stamps: measurement builds only (profiles/phase_clocks.py)
     #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[(long long)tile * 10 + (k)] = clock64(); } while (0)
+#else
+    #define T2D_STAMP(k) do { } while (0)
+#endif
     T2D_STAMP(0);
     // ------------------------------------------------------------------ load
+    // (the step counter is only needed by the status section: fetched here so that its latency is long gone by then)
+    const int cnt_in = (A.do_physics && gl == 0 && scn_ok) ? A.step_count[n] : 0;
     float sx[PPL], sy[PPL], shd[PPL], sv[PPL], svx[PPL], svy[PPL], a0[PPL], a1[PPL];
     int tidv[PPL];
 #pragma unroll
@@ -555,6 +617,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
           }
         }
       }
+    }
+    if (A.ego_action != nullptr && A.do_physics && gl == 0 && scn_ok) {   // the ego's action comes from its own [N, 2] array
+      const float2 ea = reinterpret_cast<const float2*>(A.ego_action)[n];
+      a0[0] = ea.x; a1[0] = ea.y;
     }
     if (!staged) {   // table + map tile landed? (first tile only)
       mbar_wait(s_bar, 0);
@@ -688,20 +754,18 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
     // locally for i, by atomicMin in shared memory for the partner.
     int hit[PPL];
     {
-      float thr[PPL];
+      // hot loop: every lane runs it (idle slots hold NaN and never pass); branch-free; two partners per
+      // iteration in packed fp32 (FADD2 / FFMA2).  Per pair the margin d^2 - thr is formed by two fused multiply-adds
+      // and folded into a running minimum over the 32 tests of a word (one 3-input FMNMX per partner pair); only a
+      // word whose minimum is <= 0 (rare) recomputes its verdict bits and goes to the out-of-line enqueue.
+      float2 nx2[PPL], ny2[PPL], nthr2[PPL];
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
         const float rr = rb[i] + A.rb_max;
-        thr[i] = fmaf(rr * rr, 1.00001f, 1e-12f);   // conservative: any partner's bounding radius <= rb_max
-      }
-      // hot loop: every lane runs it (idle slots hold NaN and never pass); branch-free; two partners per
-      // iteration in packed fp32 (FADD2 / FMUL2 / FFMA2).  The verdicts of four iterations are collected in one
-      // 32-bit word; a non-zero word (rare) goes to the out-of-line enqueue.
-      float2 nx2[PPL], ny2[PPL];
-#pragma unroll
-      for (int i = 0; i < PPL; ++i) {
+        const float thr = fmaf(rr * rr, 1.00001f, 1e-12f);   // conservative: any partner's bounding radius <= rb_max
         nx2[i] = make_float2(-px[i], -px[i]);
         ny2[i] = make_float2(-py[i], -py[i]);
+        nthr2[i] = make_float2(-thr, -thr);
       }
       // partner pairs u = 0 .. U-1 cover offsets -(PPL-1) .. >= Mh; U is rounded up to whole words (the extended
       // arrays are long enough), so the word body has no bounds test and its loads can be issued back to back
@@ -709,35 +773,26 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
       const int n_words = Mh > 0 ? (((Mh + PPL + 1) >> 1) + IPW - 1) / IPW : 0;
       const float2* bx = reinterpret_cast<const float2*>(posx + m0);
       const float2* by = reinterpret_cast<const float2*>(posy + m0);
-      // word 0 also meets the lane's own participants (offset <= 0): drop those verdicts up front
-      unsigned valid0 = 0;
+      if (n_words > 0) {   // word 0 also meets the lane's own participants (offset <= 0): those tests are compiled out
+        float2 X[IPW], Y[IPW];
 #pragma unroll
-      for (int uu = 0; uu < IPW; ++uu)
-#pragma unroll
-        for (int i = 0; i < PPL; ++i)
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-            if (2 * uu + e - i >= 1) valid0 |= 1u << ((uu * PPL + i) * 2 + e);
-      for (int uw = 0; uw < n_words; ++uw) {
+        for (int uu = 0; uu < IPW; ++uu) { X[uu] = bx[uu]; Y[uu] = by[uu]; }
+        if (pair_word_min<PPL, true>(X, Y, nx2, ny2, nthr2) <= 0.0f) {
+          const unsigned bits = pair_word_bits<PPL, true>(X, Y, nx2, ny2, nthr2);
+          if (bits) pair_enqueue_bits<PPL>(bits, 0, t0, tb, m0, M, Mh, queue, qcount);
+        }
+      }
+      for (int uw = 1; uw < n_words; ++uw) {
         float2 X[IPW], Y[IPW];
 #pragma unroll
         for (int uu = 0; uu < IPW; ++uu) {
           X[uu] = bx[uw * IPW + uu];
           Y[uu] = by[uw * IPW + uu];
         }
-        unsigned bits = 0;
-#pragma unroll
-        for (int uu = 0; uu < IPW; ++uu) {
-#pragma unroll
-          for (int i = 0; i < PPL; ++i) {
-            const float2 dx = __fadd2_rn(X[uu], nx2[i]), dy = __fadd2_rn(Y[uu], ny2[i]);
-            const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-            if (d2.x <= thr[i]) bits |= 1u << ((uu * PPL + i) * 2);
-            if (d2.y <= thr[i]) bits |= 2u << ((uu * PPL + i) * 2);
-          }
+        if (pair_word_min<PPL, false>(X, Y, nx2, ny2, nthr2) <= 0.0f) {
+          const unsigned bits = pair_word_bits<PPL, false>(X, Y, nx2, ny2, nthr2);
+          if (bits) pair_enqueue_bits<PPL>(bits, uw * IPW, t0, tb, m0, M, Mh, queue, qcount);
         }
-        if (uw == 0) bits &= valid0;
-        if (bits) pair_enqueue_bits<PPL>(bits, uw * IPW, t0, tb, m0, M, Mh, queue, qcount);
       }
       __syncwarp();
       T2D_STAMP(4);
@@ -835,7 +890,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
         agg = __shfl_sync(0xffffffffu, (unsigned)fl[0], sub * G);   // participant 0 = the ego
       }
       if (gl == 0 && scn_ok) {
-        const int cnt = A.step_count[n] + 1;                         // parking.py:353
+        const int cnt = cnt_in + 1;                                  // parking.py:353 (loaded with the state)
         A.step_count[n] = cnt;
         uint8_t st = T2D_STATUS_NORMAL;
         unsigned goal = 0;
@@ -854,12 +909,14 @@ __global__ void __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3)) t2d_step_kern
       }
     }
     T2D_STAMP(7);
+#if defined(T2D_DEBUG_CLOCK)
     if (A.dbg_clock && lane == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       A.dbg_clock[(long long)tile * 10 + 8] = smid;
       A.dbg_clock[(long long)tile * 10 + 9] = t_entry;
     }
+#endif
     __syncwarp();   // pose tile is reused by the next tile
   }
   if (!staged) mbar_wait(s_bar, 0);   // never leave a bulk copy in flight at exit
@@ -874,6 +931,14 @@ struct ResetArgs {
   const float *px, *py, *ph, *pv, *pvx, *pvy;
   float* goal_last_pose;
   int32_t* goal_noact_count;
+  // per-participant state owned by the world besides x .. vy: the SingleTrackDrift wheel speeds and the controllers'
+  // State.accel of the previous tick - a new episode must not inherit them from the old one
+  float *wheel_f, *wheel_r;            // [N][M] or nullptr
+  const float *pool_wf, *pool_wr;      // [n_pool][M] initial wheel speeds, or nullptr: free rolling, speed / wheel radius
+  float* last_accel;                   // [N][M] or nullptr
+  const uint8_t* type_id;
+  const Params* table;
+  int n_types;
   int N, M, n_pool;
 };
 
@@ -888,10 +953,89 @@ __global__ void t2d_reset_kernel(const __grid_constant__ ResetArgs A) {
     A.x[i] = A.px[s]; A.y[i] = A.py[s]; A.h[i] = A.ph[s]; A.v[i] = A.pv[s];
     A.vx[i] = A.pvx ? A.pvx[s] : A.pv[s] * cosf(A.ph[s]);
     A.vy[i] = A.pvy ? A.pvy[s] : A.pv[s] * sinf(A.ph[s]);
+    if (A.wheel_f != nullptr) {
+      float wf = 0.0f, wr = 0.0f;
+      if (A.pool_wf != nullptr) {
+        wf = A.pool_wf[s]; wr = A.pool_wr[s];
+      } else {
+        const int tid = A.type_id[i];
+        if (tid < A.n_types && A.table[tid].model == MODEL_DRIFT) wf = wr = A.pv[s] / A.table[tid].wheel_radius;   // zero slip
+      }
+      A.wheel_f[i] = wf; A.wheel_r[i] = wr;
+    }
+    if (A.last_accel != nullptr) A.last_accel[i] = 0.0f;   // a fresh State has no acceleration (state.py:171-185)
     if (m == 0) {
       A.step_count[n] = 0;
       if (A.goal_last_pose) A.goal_last_pose[4 * (long long)n + 3] = 0.0f;   // NoAction.reset / last_pose = None
       if (A.goal_noact_count) A.goal_noact_count[n] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- env epilogue
+// What ParkingEnv.step does after check_status (envs/parking.py:240-256, _get_reward :148-190), for all N scenarios in
+// one launch: TrafficStatus per participant from the event byte (status.py:52-61), terminated / truncated
+// (parking.py:243-248), the reward chain in the reference's order, the two running extrema it keeps per episode
+// (_max_iou, _min_dist_to_target) and the done mask that drives the masked reset.  One thread per participant slot;
+// the thread of slot 0 also does the per-scenario part.  Reads the ego's flags through the same array, so the launch
+// has no other input than the tick's outputs.
+struct EnvArgs {
+  const uint8_t* flags;        // [N][M] event byte of the tick
+  const uint8_t* status;       // [N] ScenarioStatus of the tick
+  const int32_t* step_count;   // [N]
+  const float *x, *y;          // [N][M] state after the tick (the ego's position for the distance shaping)
+  const float* iou;            // [N] IoU(ego pose, target) of the tick, or nullptr (no goal)
+  const float* target;         // [N][5] or nullptr
+  float* max_iou;              // [N] in/out, or nullptr
+  float* min_dist;             // [N] in/out, or nullptr
+  float* reward;               // [N]
+  uint8_t *terminated, *truncated, *done;   // [N]
+  uint8_t* traffic_status;     // [N][M]
+  int N, M, max_step, reset_trackers;
+};
+
+__global__ void __launch_bounds__(256) t2d_env_epilogue_kernel(const __grid_constant__ EnvArgs A) {
+  const long long total = (long long)A.N * A.M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned f = A.flags[i];
+    const uint8_t ts = (f & T2D_F_STATIC) ? 3 : ((f & T2D_F_DYNAMIC) ? 4 : 1);   // COLLISION_STATIC / COLLISION_DYNAMIC / NORMAL
+    if (A.traffic_status) A.traffic_status[i] = ts;
+    const int n = (int)(i / A.M);
+    if (i - (long long)n * A.M != 0) continue;
+    const int st = A.status[n];
+    // check_status returns at the first detector that fires (parking.py:366-385): the ego's traffic status is only set
+    // by the collision detector, i.e. when the scenario status says FAILED
+    const int ego_ts = st == T2D_STATUS_FAILED ? ts : 1;
+    const bool term = st == T2D_STATUS_COMPLETED;                                  // :243-244
+    const bool trunc = !term && (st != T2D_STATUS_NORMAL || ego_ts != 1);          // :245-248
+    float r;
+    if (ego_ts == 3 || ego_ts == 4) r = -5.0f;                                     // :151-152 (+ dynamic collision, an extension)
+    else if (st == T2D_STATUS_TIME_EXCEEDED || st == T2D_STATUS_NO_ACTION) r = -1.0f;   // :153-157
+    else if (st == T2D_STATUS_OUT_BOUND) r = -5.0f;                                // :158-159
+    else if (st == T2D_STATUS_COMPLETED) r = 5.0f;                                 // :160-161
+    else {
+      r = A.max_step > 0 ? -tanhf((float)A.step_count[n] / (float)A.max_step) * 0.001f : 0.0f;   // :163
+      if (A.iou != nullptr && A.max_iou != nullptr) {
+        const float iou = A.iou[n], best = A.max_iou[n];
+        r += (best == -INFINITY) ? iou : iou - best;                               // :164-169
+        A.max_iou[n] = fmaxf(best, iou);                                           // :170
+      }
+      if (A.target != nullptr && A.min_dist != nullptr) {
+        const float dx = A.x[i] - A.target[5 * (long long)n], dy = A.y[i] - A.target[5 * (long long)n + 1];
+        const float d = sqrtf(dx * dx + dy * dy), best = A.min_dist[n];            // :172-185
+        if (d < best) {                                                            // :186-188 (inf on the first step: the
+          if (best != INFINITY) r += (best - d) * 0.1f;                            //  reference adds inf there; we add nothing)
+          A.min_dist[n] = d;
+        }
+      }
+    }
+    A.reward[n] = r;
+    if (A.terminated) A.terminated[n] = term;
+    if (A.truncated) A.truncated[n] = trunc;
+    if (A.done) A.done[n] = term || trunc;
+    if (A.reset_trackers && (term || trunc)) {   // the next episode starts fresh (ParkingEnv.reset, parking.py:276-277)
+      if (A.max_iou) A.max_iou[n] = -INFINITY;
+      if (A.min_dist) A.min_dist[n] = INFINITY;
     }
   }
 }
@@ -908,7 +1052,8 @@ __global__ void __launch_bounds__(128) t2d_drift_kernel(const __grid_constant__ 
     if (p.model != MODEL_DRIFT) continue;
     OneIO io;
     io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = 0.0f; io.vy = 0.0f;
-    const float2 act = reinterpret_cast<const float2*>(A.action)[i];
+    float2 act = reinterpret_cast<const float2*>(A.action)[i];
+    if (A.ego_action != nullptr && i % A.M == 0) act = reinterpret_cast<const float2*>(A.ego_action)[i / A.M];
     const bool sf = (A.cfg_flags & T2D_CFG_STEER_FIRST) != 0;
     io.a0 = sf ? act.y : act.x; io.a1 = sf ? act.x : act.y;
     io.ch = 1.0f; io.sh = 0.0f;
@@ -1111,74 +1256,91 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __
 
 // ============================================================================ done exchange over peer memory
 // All-gather of the per-rank done masks as ONE small kernel per rank and step, over NVLink / NVSwitch peer memory:
-//   put     every thread stores 16-byte pieces of this rank's mask into slot (step % slots), row `rank`, of EVERY
-//           rank's gather ring (peer stores; the own ring included);
-//   signal  after a CTA barrier, thread 0 fences to system scope and writes step + 1 into word `rank` of every rank's
-//           flag array with release semantics;
-//   wait    threads 0 .. world-1 poll the OWN flag array (acquire, system scope) until every rank has signalled this
-//           step - bounded: ~2 s of SM clocks, then the sticky error word is set and the copy is skipped;
-//   copy    the slot (all ranks' masks in rank order) goes to the caller's array.
-// The kernels of one rank run in stream order and each waits for every rank's signal of the same step, so the ranks'
-// exchange streams advance in lock step and a ring of >= 2 slots is never overwritten before it has been copied out.
+//   put     warp w serves the peers w, w + warps, ...: its lanes store 16-byte pieces of this rank's mask into slot
+//           (step % slots), row `rank`, of that peer's gather ring (the own ring included);
+//   signal  every lane fences its stores to system scope, the warp synchronises and lane 0 writes step + 1 into word
+//           `rank` of the peer's flag array (a strong relaxed store behind the fence = a release): ONE fence round
+//           trip per peer, all peers in parallel - not a chain of release stores issued by one thread;
+//   wait    lanes 0 .. world-1 of warp 0 poll the OWN flag array (acquire, system scope) until every rank has signalled
+//           step - lag; bounded (`timeout` SM cycles): on expiry the sticky error word is set and dst is filled with 0xFF;
+//   copy    the slot of step - lag (all ranks' masks in rank order) goes to the caller's array.
+// lag = 0 is the synchronous all-gather (the kernel cannot retire before the slowest rank's tick of this step has
+// signalled).  lag >= 1 delivers the masks `lag` steps late: by then every signal has long arrived, the wait never spins
+// and the kernel is a few microseconds of posted stores - the exchange leaves the critical path (the consumer of the
+// gathered masks, a learner or reset scheduler, is behind the simulation anyway).  The kernels of one rank run in
+// stream order and kernel k only completes after every rank has signalled step k - lag, i.e. after every rank's kernel
+// k - lag - 1 has copied step k - 2 lag - 1 out: a ring of 2 lag + 2 slots is never overwritten before it was read.
 struct AllGatherArgs {
   unsigned char* peer[T2D_MAX_RANKS];   // every rank's exchange allocation (own included)
   unsigned char* base;                  // = peer[rank]
   const unsigned char* local;           // this rank's done mask [n_real]
   unsigned char* dst;                   // [world * n_local]
-  int world, rank, n_local, n_real, slots;
+  int world, rank, n_local, n_real, slots, lag;
+  long long timeout;                    // SM cycles the wait may spin
 };
 
-__global__ void __launch_bounds__(256) t2d_exchange_allgather_kernel(const __grid_constant__ AllGatherArgs A) {
+__global__ void __launch_bounds__(512) t2d_exchange_allgather_kernel(const __grid_constant__ AllGatherArgs A) {
   __shared__ int s_ok;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const size_t flag_off = (size_t)A.slots * A.world * A.n_local;
   unsigned* words = reinterpret_cast<unsigned*>(A.base + flag_off);      // [0, MAX_RANKS): flags; then step, -, -, error
   const unsigned step = words[T2D_MAX_RANKS];
   const size_t row = (size_t)(step % (unsigned)A.slots) * A.world * A.n_local + (size_t)A.rank * A.n_local;
   if (threadIdx.x == 0) s_ok = 1;
-  // ---- put
+  // ---- put + signal, one warp per peer
   const int n16 = A.n_local / 16;   // n_local is a multiple of 16; the tail beyond n_real is zero
-  for (int i = threadIdx.x; i < n16; i += blockDim.x) {
-    uint4 v;
-    unsigned char b[16];
+  for (int p = warp; p < A.world; p += warps) {
+    uint4* out = reinterpret_cast<uint4*>(A.peer[p] + row);
+    for (int i = lane; i < n16; i += 32) {
+      uint4 v;
+      if (16 * i + 16 <= A.n_real && (reinterpret_cast<uintptr_t>(A.local) & 15) == 0) {
+        v = __ldcg(reinterpret_cast<const uint4*>(A.local) + i);
+      } else {
+        unsigned char b[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) b[k] = (16 * i + k < A.n_real) ? A.local[16 * i + k] : (unsigned char)0;
-    memcpy(&v, b, 16);
-    for (int p = 0; p < A.world; ++p) reinterpret_cast<uint4*>(A.peer[p] + row)[i] = v;
-  }
-  __syncthreads();
-  // ---- signal
-  if (threadIdx.x == 0) {
+        for (int k = 0; k < 16; ++k) b[k] = (16 * i + k < A.n_real) ? A.local[16 * i + k] : (unsigned char)0;
+        memcpy(&v, b, 16);
+      }
+      out[i] = v;
+    }
     __threadfence_system();
-    for (int p = 0; p < A.world; ++p) {
+    __syncwarp();
+    if (lane == 0) {
       unsigned* f = reinterpret_cast<unsigned*>(A.peer[p] + flag_off) + A.rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(step + 1u) : "memory");
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(f), "r"(step + 1u) : "memory");
     }
   }
-  // ---- wait
-  if (threadIdx.x < (unsigned)A.world) {
+  // ---- wait for step - lag
+  const bool deliver = step >= (unsigned)A.lag;
+  const unsigned target = step - (unsigned)A.lag;     // the step whose masks this call delivers
+  if (deliver && threadIdx.x < (unsigned)A.world) {
     const unsigned* f = words + threadIdx.x;
     const long long t0 = clock64();
     unsigned v;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v >= step + 1u) break;
-      if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }
-      __nanosleep(32);
+      if (v >= target + 1u) break;
+      if (clock64() - t0 > A.timeout) { s_ok = 0; break; }
+      __nanosleep(20);
     }
   }
   __syncthreads();
-  if (!s_ok) {
-    if (threadIdx.x == 0) { words[T2D_MAX_RANKS + 3] = 1u; words[T2D_MAX_RANKS] = step + 1u; }
-    return;
-  }
-  // ---- copy
   const size_t bytes = (size_t)A.world * A.n_local;
-  const unsigned char* src = A.base + (size_t)(step % (unsigned)A.slots) * bytes;
-  if ((reinterpret_cast<uintptr_t>(A.dst) & 15) == 0) {
-    for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(A.dst)[i] = reinterpret_cast<const uint4*>(src)[i];
-  } else {
-    for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) A.dst[i] = src[i];
+  if (deliver) {
+    if (s_ok) {
+      // ---- copy
+      const unsigned char* src = A.base + (size_t)(target % (unsigned)A.slots) * bytes;
+      if ((reinterpret_cast<uintptr_t>(A.dst) & 15) == 0) {
+        for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
+          reinterpret_cast<uint4*>(A.dst)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
+      } else {
+        for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) A.dst[i] = __ldcg(src + i);
+      }
+    } else {
+      // a rank never showed up: the caller must not mistake stale masks for this step's - 0xFF is no done value
+      for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) A.dst[i] = (unsigned char)0xFF;
+      if (threadIdx.x == 0) words[T2D_MAX_RANKS + 3] = 1u;
+    }
   }
   if (threadIdx.x == 0) words[T2D_MAX_RANKS] = step + 1u;
 }
@@ -1204,6 +1366,7 @@ struct CtrlArgs {
   int n_paths;
   float* last_accel;
   float* action;
+  const float* ego_action;   // [N][2] or nullptr: participant 0's action (written into its row of `action` as well)
   int N, M, steer_first;
 };
 
@@ -1292,6 +1455,7 @@ __global__ void __launch_bounds__(128) t2d_control_kernel(const __grid_constant_
       if (tid >= A.n_types) continue;                  // inactive slot
       const Params& tp = A.table[tid];
       out[j] = reinterpret_cast<const float2*>(A.action)[base + m];
+      if (m == 0 && A.ego_action != nullptr) { out[j] = reinterpret_cast<const float2*>(A.ego_action)[n]; ctl[j] = true; }   // row 0 <- the ego's action
       const int cid = A.ctrl_id[base + m];
       if (cid < A.n_ctrl && A.ctab[cid].kind != T2D_CTRL_EXTERNAL) {
         const t2d_controller_params& p = A.ctab[cid];
@@ -1361,6 +1525,7 @@ struct t2d_exchange {
   size_t bytes = 0;
   int n_real = 0;
   int threads = 256;                             // CTA size of the exchange kernel (T2D_EXCHANGE_THREADS, read once at create)
+  long long timeout_cycles = 4000000000LL;       // how long a wait may spin (~2 s of SM clocks; T2D_EXCHANGE_TIMEOUT_MS)
   unsigned char* base = nullptr;                 // slots x world x n_local done bytes | MAX_RANKS flag words | step, -, -, error
   unsigned char* peer[T2D_MAX_RANKS] = {};       // every rank's base (own included), valid after t2d_exchange_connect
   bool connected = false;
@@ -1376,6 +1541,7 @@ struct t2d_ctx {
   bool has_drift = false;
   bool kin_only = false;
   float *wheel_f = nullptr, *wheel_r = nullptr;
+  const float *reset_pool_wf = nullptr, *reset_pool_wr = nullptr;   // t2d_bind_reset_wheel_pool
   Params* d_table = nullptr;
   unsigned char* d_map = nullptr;
   uint8_t* d_fine = nullptr;
@@ -1389,6 +1555,7 @@ struct t2d_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   float rb_max = 0.0f;
+  const float* ego_action = nullptr;   // t2d_set_ego_action
   const float* goal_target = nullptr;
   float* goal_iou = nullptr;
   float* goal_last_pose = nullptr;
@@ -1414,6 +1581,7 @@ struct t2d_ctx {
   // t2d_step_host: device staging for the host-resident action / status / done, the copy stream and its events
   static constexpr int MAX_HOST_CHUNKS = 8;
   float* hs_action = nullptr;          // [N][M][2]
+  float* hs_ego = nullptr;             // [N][2] (t2d_step_host_ego)
   uint8_t* hs_out = nullptr;           // [2][N] status, done
   uint8_t* hs_out_pinned = nullptr;    // pinned host mirror of hs_out
   cudaStream_t hs_copy = nullptr;
@@ -1486,6 +1654,7 @@ int t2d_destroy(t2d_ctx* c) {
   if (c->d_path_v) cudaFree(c->d_path_v);
   if (c->d_path_off) cudaFree(c->d_path_off);
   if (c->hs_action) cudaFree(c->hs_action);
+  if (c->hs_ego) cudaFree(c->hs_ego);
   if (c->hs_out) cudaFree(c->hs_out);
   if (c->hs_out_pinned) cudaFreeHost(c->hs_out_pinned);
   if (c->hs_begin) cudaEventDestroy(c->hs_begin);
@@ -1707,7 +1876,33 @@ int t2d_bind_wheel_state(t2d_ctx* c, float* omega_front, float* omega_rear) {
   return T2D_OK;
 }
 
+int t2d_bind_reset_wheel_pool(t2d_ctx* c, const float* pool_omega_front, const float* pool_omega_rear) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if ((pool_omega_front == nullptr) != (pool_omega_rear == nullptr)) return fail(T2D_E_INVALID, "t2d_bind_reset_wheel_pool: one array is NULL");
+  c->reset_pool_wf = pool_omega_front; c->reset_pool_wr = pool_omega_rear;
+  return T2D_OK;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Warps per CTA of the tick.  One wave (the usual case: every warp tile is resident at once and the kernel's duration is
+// one tile's lifetime): the SM with the most warps sets the pace, and every CTA costs a launch + prologue (barrier
+// init, TMA staging) - measured on B200 at 4096 x 64: ~0.19 us per extra warp on the fullest SM, ~0.08 us per CTA on it
+// (2 x 7 warps: 16.4 us, 7 x 2: 16.8 us, 3 x 5: 16.7 us, 2 x 8: 17.0 us, 3 x 6 - a second wave at 128 registers - 23.9 us;
+// 1-warp CTAs are far worse and are not considered).  Several waves: persistent CTAs of the largest size.
+static int pick_wpc(long long tiles, int sm_count) {
+  const int resident_warps = 14;   // per SM at the kernel's register budget, rounded down to what every variant reaches
+  if (tiles > (long long)sm_count * resident_warps) return MAX_WARPS_PER_CTA;
+  int best = 2;
+  double best_cost = 1e30;
+  for (int w = 2; w <= MAX_WARPS_PER_CTA; ++w) {
+    const long long ctas = (tiles + w - 1) / w;
+    const long long per_sm = (ctas + sm_count - 1) / sm_count;
+    const double cost = (double)(per_sm * w) + 0.42 * (double)per_sm;
+    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && w > best)) { best_cost = cost; best = w; }
+  }
+  return best;
+}
 
 // Launches K1 over the scenarios [first, first + count) of the bound state; the per-participant / per-scenario
 // pointers passed in (action, flags, ..., done) address scenario `first` already.
@@ -1727,7 +1922,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.x = c->x + p0; A.y = c->y + p0; A.h = c->h + p0; A.v = c->v + p0; A.vx = c->vx + p0; A.vy = c->vy + p0;
   A.type_id = c->type_id + p0; A.step_count = c->step_count + first;
   A.wheel_f = c->wheel_f ? c->wheel_f + p0 : nullptr; A.wheel_r = c->wheel_r ? c->wheel_r + p0 : nullptr;
-  A.action = action; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
+  A.action = action; A.ego_action = c->ego_action ? c->ego_action + 2 * (size_t)first : nullptr; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
   A.scn_status = scn_status; A.done = done;
   A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine; A.mh = c->mh;
   A.map_in_smem = (c->d_map && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
@@ -1759,12 +1954,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   const int table_bytes = (((c->n_types + 1) * (int)sizeof(Params) + 15) / 16) * 16;   // + the neutral row
   const int spw = 32 / c->G;
   const long long tiles = ((long long)count + spw - 1) / spw;
-  // warps per CTA: the largest of 8 / 4 / 2 that still leaves >= 6 CTAs per SM (small batches balance
-  // across the 148 SMs only with small CTAs; large batches amortise the map staging over more warps)
-  int wpc = 2;
-  for (int w : {8, 4}) {
-    if ((tiles + w - 1) / w >= 6LL * c->sm_count) { wpc = w; break; }
-  }
+  int wpc = pick_wpc(tiles, c->sm_count);
   if (c->wpc_override > 0) wpc = c->wpc_override;   // T2D_WPC (experiments), read once at t2d_create
   {
     int off = (A.map_in_smem ? A.map_bytes : 0) + table_bytes;
@@ -1912,6 +2102,61 @@ int t2d_step_host(t2d_ctx* c, const float* action_host, uint8_t* flags, int16_t*
   return T2D_OK;
 }
 
+int t2d_set_ego_action(t2d_ctx* c, const float* ego_action) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (ego_action && reinterpret_cast<uintptr_t>(ego_action) % 8 != 0) return fail(T2D_E_INVALID, "ego_action must be 8-byte aligned");
+  c->ego_action = ego_action;
+  return T2D_OK;
+}
+
+int t2d_step_host_ego(t2d_ctx* c, const float* ego_action_host, float* action, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment,
+                      uint8_t* scn_status_host, uint8_t* done_host, void* stream) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!ego_action_host || !action) return fail(T2D_E_INVALID, "ego_action / action is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int N = c->N;
+  if (!c->hs_ego) CUDA_TRY(cudaMalloc(&c->hs_ego, (size_t)N * 2 * sizeof(float)));
+  if (!c->hs_out) {
+    CUDA_TRY(cudaMalloc(&c->hs_out, 2 * (size_t)N));
+    CUDA_TRY(cudaMallocHost(&c->hs_out_pinned, 2 * (size_t)N));
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(c->hs_ego, ego_action_host, (size_t)N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  const float* saved = c->ego_action;
+  c->ego_action = c->hs_ego;
+  int r = T2D_OK;
+  if (c->d_ctab) r = t2d_control(c, action, stream);   // the other participants' actions never leave the device
+  if (r == T2D_OK) r = launch_step(c, action, flags, hit_index, hit_segment, c->hs_out, c->hs_out + N, stream, 1);
+  c->ego_action = saved;
+  if (r != T2D_OK) return r;
+  CUDA_TRY(cudaMemcpyAsync(c->hs_out_pinned, c->hs_out, 2 * (size_t)N, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (scn_status_host) memcpy(scn_status_host, c->hs_out_pinned, (size_t)N);
+  if (done_host) memcpy(done_host, c->hs_out_pinned + N, (size_t)N);
+  return T2D_OK;
+}
+
+int t2d_env_epilogue(t2d_ctx* c, const uint8_t* flags, const uint8_t* scn_status, float* reward, uint8_t* terminated,
+                     uint8_t* truncated, uint8_t* traffic_status, uint8_t* done, float* max_iou, float* min_dist,
+                     int reset_trackers_on_done, void* stream) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (!c->x) return fail(T2D_E_STATE, "state not bound: call t2d_bind_state first");
+  if (!flags || !scn_status || !reward) return fail(T2D_E_INVALID, "t2d_env_epilogue: flags / scn_status / reward is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  EnvArgs A{};
+  A.flags = flags; A.status = scn_status; A.step_count = c->step_count; A.x = c->x; A.y = c->y;
+  A.iou = c->goal_target ? c->goal_iou : nullptr; A.target = c->goal_target;
+  A.max_iou = max_iou; A.min_dist = min_dist;
+  A.reward = reward; A.terminated = terminated; A.truncated = truncated; A.done = done; A.traffic_status = traffic_status;
+  A.N = c->N; A.M = c->M; A.max_step = c->cfg.max_step; A.reset_trackers = reset_trackers_on_done ? 1 : 0;
+  const long long total = (long long)c->N * c->M;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
+  t2d_env_epilogue_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return T2D_OK;
+}
+
 int t2d_check_events(t2d_ctx* c, uint8_t* flags, int16_t* hit_index, int16_t* hit_segment, void* stream) {
   return launch_step(c, nullptr, flags, hit_index, hit_segment, nullptr, nullptr, stream, 0);
 }
@@ -1928,6 +2173,8 @@ int t2d_reset(t2d_ctx* c, const uint8_t* mask, const int32_t* pool_index, int n_
   A.mask = mask; A.pool_index = pool_index;
   A.px = pool_x; A.py = pool_y; A.ph = pool_heading; A.pv = pool_speed; A.pvx = pool_vx; A.pvy = pool_vy;
   A.goal_last_pose = c->goal_last_pose; A.goal_noact_count = c->goal_noact_count;
+  A.wheel_f = c->wheel_f; A.wheel_r = c->wheel_r; A.pool_wf = c->reset_pool_wf; A.pool_wr = c->reset_pool_wr;
+  A.last_accel = c->ctrl_last_accel; A.type_id = c->type_id; A.table = c->d_table; A.n_types = c->n_types;
   A.N = c->N; A.M = c->M; A.n_pool = n_pool;
   const long long total = (long long)c->N * c->M;
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
@@ -2026,7 +2273,7 @@ int t2d_control(t2d_ctx* c, float* action, void* stream) {
   A.x = c->x; A.y = c->y; A.h = c->h; A.v = c->v; A.type_id = c->type_id; A.table = c->d_table; A.n_types = c->n_types;
   A.ctab = c->d_ctab; A.n_ctrl = c->n_ctrl; A.ctrl_id = c->ctrl_id; A.lead = c->ctrl_lead; A.path_id = c->ctrl_path;
   A.path_v = c->d_path_v; A.path_off = c->d_path_off; A.n_paths = c->n_paths;
-  A.last_accel = c->ctrl_last_accel; A.action = action;
+  A.last_accel = c->ctrl_last_accel; A.action = action; A.ego_action = c->ego_action;
   A.N = c->N; A.M = c->M; A.steer_first = (c->cfg.flags & T2D_CFG_STEER_FIRST) ? 1 : 0;
   const int warps_per_cta = 4;
   const int grid = std::max(1, std::min((c->N + warps_per_cta - 1) / warps_per_cta, c->sm_count * 16));
@@ -2045,9 +2292,14 @@ int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int
   CUDA_TRY(cudaSetDevice(device));
   t2d_exchange* x = new t2d_exchange();
   x->device = device; x->world = world; x->rank = rank; x->n_real = n_local; x->n_local = (n_local + 15) & ~15; x->slots = slots;
+  x->threads = std::min(256, 32 * world);                 // one warp per peer
   if (const char* e = getenv("T2D_EXCHANGE_THREADS")) {   // experiments: a smaller CTA finds a home on a busy SM sooner
     const int v = atoi(e);
-    if (v >= 32 && v <= 256 && v % 32 == 0 && v >= world) x->threads = v;
+    if (v >= 32 && v <= 512 && v % 32 == 0 && v >= world) x->threads = v;
+  }
+  if (const char* e = getenv("T2D_EXCHANGE_TIMEOUT_MS")) {
+    const double ms = atof(e);
+    if (ms > 0.0) x->timeout_cycles = (long long)(ms * 2.0e6);   // ~2 GHz SM clock
   }
   x->bytes = x->flag_off() + (T2D_MAX_RANKS + 4) * sizeof(unsigned);
   cudaError_t e = cudaMalloc(&x->base, x->bytes);
@@ -2073,26 +2325,36 @@ int t2d_exchange_connect(t2d_exchange* x, const void* handles) {
     cudaIpcMemHandle_t h;
     memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)p * sizeof(h), sizeof(h));
     void* ptr = nullptr;
-    CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {   // do not leak the mappings opened so far
+      for (int q = 0; q < p; ++q)
+        if (q != x->rank && x->peer[q]) { cudaIpcCloseMemHandle(x->peer[q]); x->peer[q] = nullptr; }
+      return fail(T2D_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
     x->peer[p] = static_cast<unsigned char*>(ptr);
   }
   x->connected = true;
   return T2D_OK;
 }
 
-int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, void* stream) {
+int t2d_exchange_allgather_lagged(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, int lag, void* stream) {
   if (!x || !done_local || !dst) return fail(T2D_E_INVALID, "exchange / done_local / dst is NULL");
   if (!x->connected) return fail(T2D_E_STATE, "exchange not connected: call t2d_exchange_connect first");
+  if (lag < 0 || 2 * lag + 2 > x->slots) return fail(T2D_E_INVALID, "lag needs a ring of at least 2 * lag + 2 slots");
   CUDA_TRY(cudaSetDevice(x->device));
   AllGatherArgs A{};
   for (int p = 0; p < x->world; ++p) A.peer[p] = x->peer[p];
   A.base = x->base; A.local = done_local; A.dst = dst;
   A.world = x->world; A.rank = x->rank; A.n_local = x->n_local; A.n_real = x->n_real; A.slots = x->slots;
-  const int threads = x->threads;
-  t2d_exchange_allgather_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(A);
+  A.lag = lag; A.timeout = x->timeout_cycles;
+  t2d_exchange_allgather_kernel<<<1, x->threads, 0, (cudaStream_t)stream>>>(A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return T2D_OK;
+}
+
+int t2d_exchange_allgather(t2d_exchange* x, const uint8_t* done_local, uint8_t* dst, void* stream) {
+  return t2d_exchange_allgather_lagged(x, done_local, dst, 0, stream);
 }
 
 int t2d_exchange_status(t2d_exchange* x, uint32_t* steps, uint32_t* timed_out) {

@@ -70,9 +70,13 @@ class PeerDoneExchange:
     every rank (peer stores over NVLink / NVSwitch), signals the step on every rank's flag word, waits for all ranks'
     signals and copies the slot out (``t2d_exchange_*`` in ``include/t2d_b200.h``).  Equal shards, one node.
     ``torch.distributed`` is used once, to pass the CUDA IPC handles around.  Call it like ``DoneExchange``:
-    ``done_all = exchange(out.done)`` on every rank, the same number of times, in stream order."""
+    ``done_all = exchange(out.done)`` on every rank, the same number of times, in stream order.
 
-    def __init__(self, n_local: int, device, slots: int = 4, group=None, lib=None):
+    ``lag`` > 0 takes the exchange off the critical path: call k posts step k's mask and returns the gathered masks of
+    step k - lag (the first ``lag`` calls leave the output untouched); nothing waits for the slowest rank's current
+    tick any more.  ``slots`` defaults to the 2 * lag + 2 the ring needs."""
+
+    def __init__(self, n_local: int, device, slots: Optional[int] = None, group=None, lib=None, lag: int = 0):
         import ctypes as C
 
         import torch
@@ -86,14 +90,23 @@ class PeerDoneExchange:
         self.rank = dist.get_rank(group)
         self.n_local = int(n_local)
         self.pad = (self.n_local + 15) & ~15
-        self.slots = int(slots)
+        self.lag = int(lag)
+        if self.lag < 0:
+            raise ValueError("lag must be >= 0")
+        self.slots = int(slots) if slots is not None else max(4, 2 * self.lag + 2)
+        if self.slots < 2 * self.lag + 2:
+            raise ValueError("a lag of k steps needs a ring of at least 2 k + 2 slots")
+        self.calls = 0
+        dev_index = self.device.index
+        if dev_index is None:   # an un-indexed 'cuda' device is the CURRENT device, not GPU 0
+            dev_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self._x = C.c_void_p()
         handle = (C.c_ubyte * 64)()
         # Every step of the set-up is agreed on by all ranks before anybody proceeds: a rank whose CUDA IPC call fails
         # (no peer access, a container without shared IPC namespaces) must not leave the others waiting in a collective.
         problem = None
         try:
-            _lib.check(self.lib.t2d_exchange_create(C.byref(self._x), self.device.index or 0, self.world_size, self.rank, self.n_local,
+            _lib.check(self.lib.t2d_exchange_create(C.byref(self._x), dev_index, self.world_size, self.rank, self.n_local,
                                                     self.slots, C.cast(handle, C.c_void_p)))
         except Exception as e:   # noqa: BLE001 - reported to every rank below
             problem = f"create: {e}"
@@ -115,8 +128,9 @@ class PeerDoneExchange:
         self.out = torch.zeros(self.world_size * self.pad, dtype=torch.uint8, device=self.device)
 
     def __call__(self, done_local, out=None):
-        """``done_local``: uint8 [n_local] on this rank -> uint8 [world * pad] (row r = rank r's mask, zero padded);
-        enqueued on the current stream."""
+        """``done_local``: uint8 [n_local] on this rank -> uint8 [world * pad] (row r = rank r's mask, zero padded) of the
+        step ``lag`` calls ago (this step's with ``lag`` = 0); enqueued on the current stream.  A row of 0xFF bytes
+        means a rank failed to signal within the time-out (``status()`` then reports ``timed_out``)."""
         import ctypes as C
 
         import torch
@@ -127,7 +141,9 @@ class PeerDoneExchange:
             raise ValueError("done_local must be a contiguous uint8 tensor of this rank's scenarios")
         out = self.out if out is None else out
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(self.lib.t2d_exchange_allgather(self._x, C.c_void_p(done_local.data_ptr()), C.c_void_p(out.data_ptr()), stream))
+        _lib.check(self.lib.t2d_exchange_allgather_lagged(self._x, C.c_void_p(done_local.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                          self.lag, stream))
+        self.calls += 1
         return out
 
     def status(self):

@@ -11,8 +11,12 @@ Keeps the contract of the reference's single-ego envs (``tactics2d/envs/parking.
   status is not NORMAL (parking.py:243-248); without a ``target`` a scenario never completes, so every ``done``
   is a truncation;
 * the status priority time-exceed -> out-of-bound -> collision (parking.py:361-392);
-* reward shape of ``ParkingEnv._get_reward`` (parking.py:148-190) for the events that exist here:
-  -5 collision / out-of-bound, -1 time exceeded, else a small time penalty ``-tanh(t / max_step) * 0.001``.
+* the reward chain of ``ParkingEnv._get_reward`` (parking.py:148-190), in its order: -5 collision, -1 time exceeded / no
+  action, -5 out of bound, +5 completed, else the time penalty ``-tanh(t / max_step) * 0.001`` + the IoU gain over the
+  episode's best + 0.1 x the progress towards the target centre (``_max_iou`` / ``_min_dist_to_target`` are kept per
+  scenario on the device).  Two deliberate differences, both where the reference misbehaves: its check_status stores
+  NO_ACTION into the *traffic* status (parking.py:372), here it is a scenario status and earns the -1 the reward chain
+  intends; its first step adds ``(inf - d) * 0.1`` to the reward, here the first step only records the distance.
 
 What differs, deliberately: the environment is *vectorised* (every quantity has a leading N axis and lives on
 the GPU), all M participants are simulated (the ego is participant 0; the others take ``npc_action`` or zeros),
@@ -64,10 +68,8 @@ class BatchedTrafficEnv:
         self.scenario_manager.set_initial_state(self._pool)
         self._action = torch.zeros((n, m, 2), dtype=torch.float32, device=dev)
         self._rng = np.random.default_rng(0)
-        self._max_iou = None
         if target is not None:
             self.world.set_goal(target, arrival_threshold, no_action_max_step)
-            self._max_iou = torch.full((n,), -float("inf"), dtype=torch.float32, device=dev)
         self.observation_space = {"shape": (n, m, 6), "dtype": "float32"}
         self.action_space = {"shape": (n, 2), "low": (-np.inf, -np.inf), "high": (np.inf, np.inf)}
 
@@ -90,8 +92,7 @@ class BatchedTrafficEnv:
             perm = torch.from_numpy(self._rng.permutation(self.num_envs).astype(np.int32)).to(self.world.device)
         self.world.type_id.copy_(self._type_id)
         self.scenario_manager.reset(pool_index=perm)
-        if self._max_iou is not None:
-            self._max_iou.fill_(-float("inf"))
+        self.world.reset_env_trackers()
         status = torch.full((self.num_envs,), int(ScenarioStatus.NORMAL), dtype=torch.uint8, device=self.world.device)
         traffic = torch.full((self.num_envs, self.num_participants), int(TrafficStatus.NORMAL), dtype=torch.uint8,
                              device=self.world.device)
@@ -101,54 +102,37 @@ class BatchedTrafficEnv:
 
     def step(self, action, npc_action=None):
         """``action``: fp32 device tensor [N, 2] = (steering, accel) of the ego (participant 0), or [N, M, 2] for
-        all participants; ``npc_action`` [N, M-1, 2] optionally drives the others."""
-        import torch
+        all participants; ``npc_action`` [N, M-1, 2] optionally drives the others (otherwise they keep their rows of the
+        internal action array: zeros, or what ``world.set_controllers`` computes on the device every tick).
 
+        Launches per call: the controllers (if set), the fused tick, the env epilogue (reward / terminated / truncated /
+        TrafficStatus / done in one kernel) and the masked reset - no elementwise PyTorch.  The tensors in the returned
+        tuple and in ``info`` are views of buffers owned by the env: they hold this step's values until the next ``step``."""
+        w = self.world
         if action.dim() == 3:
             if tuple(action.shape) != (self.num_envs, self.num_participants, 2):
                 raise InvalidAction(f"Action of shape {tuple(action.shape)} is not in the action space.")
             full = action.contiguous()
+            w.set_ego_action(None)
         else:
             if tuple(action.shape) != (self.num_envs, 2):
                 raise InvalidAction(f"Action of shape {tuple(action.shape)} is not in the action space.")
             full = self._action
-            full[:, 0, :] = action
+            w.set_ego_action(action.to(device=w.device, dtype=full.dtype).contiguous())   # read by the kernels, not scattered
             if npc_action is not None:
                 full[:, 1:, :] = npc_action
+        if w.last_accel is not None:
+            w.control(full)
         self.scenario_manager.update(full)
         status, traffic = self.scenario_manager.check_status()
-        r = self.world._out
-        terminated = status == int(ScenarioStatus.COMPLETED)
-        truncated = (~terminated) & ((status != int(ScenarioStatus.NORMAL)) | (traffic[:, 0] != int(TrafficStatus.NORMAL)))
-        reward = self._get_reward(status, traffic[:, 0])
-        info = self._info(status.clone(), traffic, r.flags.clone(), r.hit_index.clone(), r.hit_segment.clone())
+        e = self.scenario_manager.env_result
+        r = w.result
+        info = self._info(status, traffic, r.flags, r.hit_index, r.hit_segment)
         if r.iou is not None:
-            info["iou"] = r.iou.clone()
+            info["iou"] = r.iou
         if self.auto_reset:
-            done = (terminated | truncated).to(torch.uint8)
-            self.scenario_manager.reset(mask=done)
-            if self._max_iou is not None:
-                self._max_iou = torch.where(done.bool(), torch.full_like(self._max_iou, -float("inf")), self._max_iou)
-        return self._obs(), reward, terminated, truncated, info
-
-    def _get_reward(self, scenario_status, ego_traffic_status):
-        """parking.py:148-190 restricted to the events of this path."""
-        import torch
-
-        t = self.world.step_count.to(torch.float32)
-        reward = -torch.tanh(t / float(self.max_step)) * 0.001
-        iou = self.world._out.iou
-        if iou is not None:   # parking.py:166-172: first the IoU itself, then its improvement over the best so far
-            first = torch.isinf(self._max_iou)
-            reward = reward + torch.where(first, iou, iou - self._max_iou)
-            self._max_iou = torch.maximum(self._max_iou, iou)
-            reward = torch.where(scenario_status == int(ScenarioStatus.COMPLETED), torch.full_like(reward, 5.0), reward)
-            reward = torch.where(scenario_status == int(ScenarioStatus.NO_ACTION), torch.full_like(reward, -1.0), reward)
-        reward = torch.where(scenario_status == int(ScenarioStatus.TIME_EXCEEDED), torch.full_like(reward, -1.0), reward)
-        reward = torch.where(scenario_status == int(ScenarioStatus.OUT_BOUND), torch.full_like(reward, -5.0), reward)
-        collided = (ego_traffic_status == int(TrafficStatus.COLLISION_STATIC)) | (ego_traffic_status == int(TrafficStatus.COLLISION_DYNAMIC))
-        collided = collided & (scenario_status == int(ScenarioStatus.FAILED))
-        return torch.where(collided, torch.full_like(reward, -5.0), reward)
+            self.scenario_manager.reset(mask=e.done)
+        return self._obs(), e.reward, e.terminated, e.truncated, info
 
     def render(self):
         raise NotImplementedError("rendering is outside this hot path")

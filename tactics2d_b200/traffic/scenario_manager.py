@@ -62,6 +62,8 @@ class BatchedScenarioManager(ScenarioManager):
         world.set_config(interval=self.step_size, max_step=self.max_step or 0)
         self._initial = None
         self._last = None
+        self.env_result = None
+        self.reset_trackers_on_done = True
 
     def set_initial_state(self, pool: dict):
         """Pool of initial states ``x, y, heading, speed[, vx, vy]`` [P, M] (device) that ``reset`` draws from."""
@@ -73,14 +75,12 @@ class BatchedScenarioManager(ScenarioManager):
         return self.get_observation()
 
     def check_status(self):
-        import torch
-
+        """(scenario_status [N], traffic_status [N, M]) of the last tick.  The priority chain itself ran inside the tick
+        (parking.py:361-392); the TrafficStatus codes come from ``t2d_env_epilogue`` - one launch that also leaves the
+        reward / terminated / truncated / done vectors of ``ParkingEnv.step`` in ``self.env_result``."""
         r = self._last if self._last is not None else self.world.check_events()
-        f = r.flags
-        traffic = torch.full_like(f, int(TrafficStatus.NORMAL))
-        traffic = torch.where((f & 1) != 0, torch.full_like(f, int(TrafficStatus.COLLISION_DYNAMIC)), traffic)
-        traffic = torch.where((f & 2) != 0, torch.full_like(f, int(TrafficStatus.COLLISION_STATIC)), traffic)
-        return r.status, traffic
+        self.env_result = self.world.env_epilogue(reset_trackers_on_done=self.reset_trackers_on_done)
+        return r.status, self.env_result.traffic_status
 
     def get_observation(self):
         w = self.world

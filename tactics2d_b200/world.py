@@ -39,6 +39,17 @@ class StepResult:
     iou: Optional[torch.Tensor] = None   # fp32 [N]: IoU(ego pose, target area) when a goal is set (Arrival.update)
 
 
+@dataclass
+class EnvResult:
+    """Device tensors written by ``env_epilogue`` (views of buffers owned by the world, overwritten by the next call)."""
+
+    reward: torch.Tensor          # fp32 [N]
+    terminated: torch.Tensor      # bool [N]
+    truncated: torch.Tensor       # bool [N]
+    done: torch.Tensor            # uint8 [N] = terminated | truncated (the mask ``reset`` takes)
+    traffic_status: torch.Tensor  # uint8 [N, M] TrafficStatus codes
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -292,6 +303,70 @@ class BatchedWorld:
         self.frame += self.interval
         return hb[0], hb[1]
 
+    # ------------------------------------------------------------------ env layer
+    def set_ego_action(self, ego_action: Optional[torch.Tensor]):
+        """Bind the ego's action array: fp32 device tensor [N, 2] (or None to unbind).  While bound, ``control`` and
+        ``step`` take the action of participant 0 of every scenario from it - the reference env's single action
+        (envs/parking.py:219-239) - instead of row 0 of the full action array."""
+        if ego_action is not None:
+            if (ego_action.device != self.device or ego_action.dtype != torch.float32 or tuple(ego_action.shape) != (self.N, 2)
+                    or not ego_action.is_contiguous()):
+                raise ValueError(f"ego_action must be a contiguous fp32 [{self.N}, 2] tensor on {self.device}")
+        self._ego_action = ego_action   # keeps the tensor alive while the library holds its pointer
+        _lib.check(self.lib.t2d_set_ego_action(self._ctx, _ptr(ego_action)))
+
+    def step_host_ego(self, ego_action, action: Optional[torch.Tensor] = None):
+        """One tick for a host-side policy that drives only the ego: ``ego_action`` is a float32 ``[N, 2]`` NumPy array
+        or CPU tensor; the other participants take the rows of the DEVICE array ``action`` [N, M, 2] (default: an
+        internal zero array), which ``set_controllers`` fills on the device.  Per step 8 N bytes go up and 2 N come back
+        (``t2d_step_host_ego``).  Returns ``(done, status)`` as uint8 NumPy arrays [N]."""
+        a = ego_action if isinstance(ego_action, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ego_action, dtype=np.float32))
+        if a.device.type != "cpu" or a.dtype != torch.float32 or tuple(a.shape) != (self.N, 2) or not a.is_contiguous():
+            raise ValueError(f"ego_action must be a contiguous float32 host array [{self.N}, 2]")
+        if action is None:
+            action = getattr(self, "_npc_action", None)
+            if action is None:
+                action = self._npc_action = torch.zeros((self.N, self.M, 2), dtype=torch.float32, device=self.device)
+        elif action.device != self.device or action.dtype != torch.float32 or tuple(action.shape) != (self.N, self.M, 2) \
+                or not action.is_contiguous():
+            raise ValueError(f"action must be contiguous fp32 [{self.N}, {self.M}, 2] on {self.device}")
+        hb = getattr(self, "_host_out", None)
+        if hb is None:
+            hb = self._host_out = (np.empty(self.N, np.uint8), np.empty(self.N, np.uint8))
+        o = self._out
+        _lib.check(self.lib.t2d_step_host_ego(self._ctx, a.data_ptr(), _ptr(action), _ptr(o.flags), _ptr(o.hit_index),
+                                              _ptr(o.hit_segment), hb[1].ctypes.data, hb[0].ctypes.data, self._stream()))
+        self.frame += self.interval
+        return hb[0], hb[1]
+
+    def env_epilogue(self, reset_trackers_on_done: bool = True) -> "EnvResult":
+        """Reward, terminated, truncated, done and the per-participant TrafficStatus of the last tick in ONE launch
+        (``t2d_env_epilogue``: ParkingEnv.step after check_status, envs/parking.py:240-256 and _get_reward :148-190)."""
+        e = getattr(self, "_env", None)
+        if e is None:
+            u8 = dict(dtype=torch.uint8, device=self.device)
+            e = self._env = dict(
+                reward=torch.zeros(self.N, dtype=torch.float32, device=self.device),
+                terminated=torch.zeros(self.N, dtype=torch.bool, device=self.device),
+                truncated=torch.zeros(self.N, dtype=torch.bool, device=self.device),
+                done=torch.zeros(self.N, **u8), traffic=torch.ones((self.N, self.M), **u8),
+                max_iou=torch.full((self.N,), -float("inf"), dtype=torch.float32, device=self.device),
+                min_dist=torch.full((self.N,), float("inf"), dtype=torch.float32, device=self.device))
+        goal = self._goal is not None
+        o = self._out
+        _lib.check(self.lib.t2d_env_epilogue(self._ctx, _ptr(o.flags), _ptr(o.status), _ptr(e["reward"]), _ptr(e["terminated"]),
+                                             _ptr(e["truncated"]), _ptr(e["traffic"]), _ptr(e["done"]),
+                                             _ptr(e["max_iou"] if goal else None), _ptr(e["min_dist"] if goal else None),
+                                             1 if reset_trackers_on_done else 0, self._stream()))
+        return EnvResult(e["reward"], e["terminated"], e["truncated"], e["done"], e["traffic"])
+
+    def reset_env_trackers(self):
+        """``ParkingEnv.reset``: forget the best IoU / distance of the previous episodes (parking.py:276-277)."""
+        e = getattr(self, "_env", None)
+        if e is not None:
+            e["max_iou"].fill_(-float("inf"))
+            e["min_dist"].fill_(float("inf"))
+
     def check_events(self) -> StepResult:
         """The detectors on the current poses, no physics (``EventBase.update``)."""
         o = self._out
@@ -318,16 +393,28 @@ class BatchedWorld:
         parking.py:397-441; ``ParticipantBase.reset``, participant_base.py:236-246)."""
         px = pool["x"]
         n_pool = px.shape[0]
-        for k in ("x", "y", "heading", "speed"):
+        cols = ["x", "y", "heading", "speed"] + [k for k in ("vx", "vy", "omega_wf", "omega_wr") if pool.get(k) is not None]
+        for k in cols:
             t = pool[k]
-            if t.device != self.device or t.dtype != torch.float32 or tuple(t.shape) != (n_pool, self.M):
-                raise ValueError(f"pool[{k!r}] must be fp32 [{n_pool}, {self.M}] on {self.device}")
-        if mask.dtype != torch.uint8:
-            mask = mask.to(torch.uint8)
-        if pool_index is not None and pool_index.dtype != torch.int32:
-            pool_index = pool_index.to(torch.int32)
+            if t.device != self.device or t.dtype != torch.float32 or tuple(t.shape) != (n_pool, self.M) or not t.is_contiguous():
+                raise ValueError(f"pool[{k!r}] must be a contiguous fp32 [{n_pool}, {self.M}] tensor on {self.device}")
+        if (pool.get("vx") is None) != (pool.get("vy") is None):
+            raise ValueError("give both pool['vx'] and pool['vy'], or neither")
+        # mask / pool_index reach the kernel as raw pointers: a host tensor or a wrong length would be an illegal address
+        if not torch.is_tensor(mask) or mask.numel() != self.N:
+            raise ValueError(f"mask must be a tensor of {self.N} scenarios")
+        mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if pool_index is not None:
+            if not torch.is_tensor(pool_index) or pool_index.numel() != self.N:
+                raise ValueError(f"pool_index must be a tensor of {self.N} scenarios")
+            pool_index = pool_index.to(device=self.device, dtype=torch.int32).contiguous()
         if pool_index is None and n_pool < self.N:
             raise ValueError("without pool_index the pool needs one row per scenario")
+        if self.omega_front is not None:
+            wf, wr = pool.get("omega_wf"), pool.get("omega_wr")
+            if (wf is None) != (wr is None):
+                raise ValueError("give both pool['omega_wf'] and pool['omega_wr'], or neither")
+            _lib.check(self.lib.t2d_bind_reset_wheel_pool(self._ctx, _ptr(wf), _ptr(wr)))
         _lib.check(self.lib.t2d_reset(self._ctx, _ptr(mask), _ptr(pool_index), n_pool, _ptr(pool["x"]), _ptr(pool["y"]),
                                       _ptr(pool["heading"]), _ptr(pool["speed"]), _ptr(pool.get("vx")),
                                       _ptr(pool.get("vy")), self._stream()))

@@ -65,6 +65,25 @@ def main():
             torch.cuda.synchronize()
             assert torch.equal(outs[i].view(world, ex.pad)[:, :n].reshape(-1), ref), (rank, rep, i)
     assert ex.status() == (7 + 18, 0), ex.status()
+    # lagged delivery: call k posts step k's mask and returns the gathered masks of step k - lag (off the critical path)
+    for lag in (1, 2):
+        exl = PeerDoneExchange(n, dev, lag=lag)
+        hist = []
+        sentinel = torch.full((world * exl.pad,), 7, dtype=torch.uint8, device=dev)
+        for t in range(9):
+            act = torch.from_numpy(synthetic.random_actions(5000 * lag + 1000 * rank + t, (n, m))).to(dev)
+            out = w.step(act)
+            buf = sentinel.clone()
+            got = exl(out.done, buf).clone()
+            dist.all_gather_into_tensor(ref, out.done)
+            torch.cuda.synchronize()
+            hist.append(ref.clone())
+            if t < lag:
+                assert torch.equal(got, sentinel), (rank, lag, t)          # nothing delivered yet: dst untouched
+            else:
+                assert torch.equal(got.view(world, exl.pad)[:, :n].reshape(-1), hist[t - lag]), (rank, lag, t)
+        assert exl.status() == (9, 0), exl.status()
+        exl.close()
     dist.barrier()
     if rank == 0:
         print("EXCHANGE_OK", world)

@@ -225,6 +225,94 @@ def test_batched_env_contract(cuda_device):
     env.close()
 
 
+def test_env_epilogue_matches_reference_reward_chain(cuda_device):
+    """reward / terminated / truncated / done / TrafficStatus of t2d_env_epilogue against the float64 restatement of
+    ParkingEnv.step + _get_reward (envs/parking.py:148-190, 240-256), over a free rollout with a target (IoU gain and
+    distance-to-target shaping with their per-episode extrema) and with every terminal status occurring."""
+    import torch
+
+    from oracle import scenario as O
+    from tactics2d_b200 import BatchedWorld, synthetic
+
+    n, m = 96, 8
+    scene = synthetic.config2(n, m, seed=21, size=40.0)
+    tab = scene.table.as_oracle_table()
+    tid0 = scene.type_id[:, 0]
+    rng = np.random.default_rng(4)
+    speed = scene.speed.copy()
+    speed[:32, 0] = 0.0                 # egos 0..31 stand still (zero action below): parked ones arrive, the others idle
+    w = BatchedWorld(n, m, scene.table, device=cuda_device, max_step=6, steer_first=True)
+    w.set_map(scene.segments, scene.bounds)
+    w.set_state(scene.x, scene.y, scene.heading, speed, type_id=scene.type_id)
+    target = np.stack([scene.x[:, 0] + rng.uniform(-3, 3, n), scene.y[:, 0] + rng.uniform(-3, 3, n), scene.heading[:, 0],
+                       tab["half_len"][tid0], tab["half_wid"][tid0]], 1).astype(np.float32)
+    target[:8, :3] = np.stack([scene.x[:8, 0], scene.y[:8, 0], scene.heading[:8, 0]], 1)   # egos 0..7 are already parked
+    w.set_goal(target, 0.95, 3)
+    max_iou = np.full(n, -np.inf)
+    min_dist = np.full(n, np.inf)
+    seen = set()
+    for t in range(9):
+        act = torch.from_numpy(synthetic.random_actions(300 + t, (n, m))).to(cuda_device)
+        act[:32, 0, :] = 0.0
+        out = w.step(act)
+        e = w.env_epilogue(reset_trackers_on_done=True)
+        torch.cuda.synchronize()
+        ref = O.env_epilogue(out.flags.cpu().numpy(), out.status.cpu().numpy(), w.step_count.cpu().numpy(), 6,
+                             iou=out.iou.cpu().numpy().astype(np.float64),
+                             ego_xy=np.stack([w.x[:, 0].cpu().numpy(), w.y[:, 0].cpu().numpy()], 1).astype(np.float64),
+                             target=target.astype(np.float64), max_iou=max_iou, min_dist=min_dist)
+        max_iou, min_dist = ref["max_iou"], ref["min_dist"]
+        assert np.array_equal(e.terminated.cpu().numpy(), ref["terminated"])
+        assert np.array_equal(e.truncated.cpu().numpy(), ref["truncated"])
+        assert np.array_equal(e.done.cpu().numpy(), ref["done"])
+        assert np.array_equal(e.traffic_status.cpu().numpy(), ref["traffic_status"])
+        np.testing.assert_allclose(e.reward.cpu().numpy(), ref["reward"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(w._env["max_iou"].cpu().numpy(), max_iou, rtol=1e-6)
+        np.testing.assert_allclose(w._env["min_dist"].cpu().numpy(), min_dist, rtol=1e-6)
+        seen |= set(np.unique(out.status.cpu().numpy()).tolist())
+    assert {1, 2, 3, 5, 6} <= seen, seen     # NORMAL, COMPLETED, TIME_EXCEEDED, NO_ACTION, FAILED all occurred
+    w.close()
+
+
+def test_step_host_ego_equals_device_step(cuda_device):
+    """t2d_step_host_ego (host [N, 2] ego actions up, status + done back; the other rows stay on the device) = set_ego_action
+    + control + step with device tensors."""
+    import torch
+
+    from tactics2d_b200 import BatchedWorld, synthetic
+    from tactics2d_b200.controller import IDMController
+
+    n, m = 80, 12
+    scene = synthetic.config2(n, m, seed=31, size=60.0)
+    worlds = []
+    for _ in range(2):
+        w = BatchedWorld(n, m, scene.table, device=cuda_device, max_step=50, steer_first=True)
+        w.set_map(scene.segments, scene.bounds)
+        w.set_state(scene.x, scene.y, scene.heading, scene.speed, type_id=scene.type_id)
+        cid = np.zeros((n, m), np.uint8); cid[:, 0] = 255          # the ego is driven from outside
+        lead = np.tile(np.arange(m, dtype=np.int16) - 1, (n, 1))
+        w.set_controllers([IDMController()], cid, lead_index=lead)
+        worlds.append(w)
+    wa, wb = worlds
+    act_a = torch.zeros((n, m, 2), device=cuda_device)
+    act_b = torch.zeros((n, m, 2), device=cuda_device)
+    for t in range(5):
+        ego = synthetic.random_actions(700 + t, (n, 1))[:, 0, ::-1].copy()    # (steer, accel)
+        done, status = wa.step_host_ego(ego, act_a)
+        wb.set_ego_action(torch.from_numpy(ego).to(cuda_device))
+        wb.control(act_b)
+        out = wb.step(act_b)
+        torch.cuda.synchronize()
+        assert np.array_equal(done, out.done.cpu().numpy()) and np.array_equal(status, out.status.cpu().numpy())
+        for k in ("x", "y", "heading", "speed"):
+            assert torch.equal(getattr(wa, k), getattr(wb, k)), (t, k)
+        assert torch.equal(act_a, act_b) and torch.equal(act_a[:, 0, :].cpu(), torch.from_numpy(ego))
+        assert torch.equal(wa.result.flags, out.flags)
+    # the ego really took its own action: a world stepped with a zero ego action differs
+    for w in worlds:
+        w.close()
+
+
 def test_arrival_and_no_action_detectors(cuda_device):
     """Arrival (IoU >= 0.95 -> COMPLETED) and NoAction (pose IoU > 0.999 for more than max_step ticks -> NO_ACTION)
     for the ego of every scenario, against the float64 oracle; status priority of envs/parking.py:361-392."""
