@@ -190,11 +190,11 @@ __device__ __noinline__ bool oob_exact(const Pose a, float xmin, float xmax, flo
 // pushed the whole kernel into spilling and cost the other models 3 - 9 %), so t2d_drift_kernel advances those
 // participants in a pre-pass and K1 only builds their pose.
 __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_steps, double dt, double dt_rem, double interval) {
-  if (p.model == MODEL_DYNAMICS) {
+  if (p.model() == MODEL_DYNAMICS) {
     dynamics_step(io, p, n_steps, dt);
-  } else if (p.model == MODEL_POINTMASS_NEWTON) {
+  } else if (p.model() == MODEL_POINTMASS_NEWTON) {
     pointmass_newton_step(io, p, interval);
-  } else if (p.model == MODEL_POINTMASS_EULER) {
+  } else if (p.model() == MODEL_POINTMASS_EULER) {
     pointmass_euler_step(io, p, n_steps, dt, dt_rem);
   } else {
     sincos_fast(io.h, &io.sh, &io.ch);
@@ -239,7 +239,13 @@ __device__ __forceinline__ bool near_segments(const float ax, const float ay, co
 
 // Own pose of participant `idx` back from the warp's shared-memory tile (the hot loops keep only x, y
 // and the bounding radius in registers; the rare exact paths re-read the rest).
-__device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* poseB, int idx) {
+// The warp's pose tile is addressed by participant slot (scenario slot x padded participants + participant), but laid
+// out lane-minor: slot = lane * PPL + i lives at word i * 32 + lane, so that the lanes' stores of their own PPL
+// participants are conflict-free (consecutive lanes, consecutive 16-byte words).  psh = log2(PPL).
+__device__ __forceinline__ int pslot(int slot, int psh) { return ((slot & ((1 << psh) - 1)) << 5) | (slot >> psh); }
+
+__device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* poseB, int slot, int psh) {
+  const int idx = pslot(slot, psh);
   const float4 a = poseA[idx], b = poseB[idx];
   Pose p;
   p.x = a.x; p.y = a.y; p.h = a.w; p.c = b.x; p.s = b.y; p.l = b.z; p.w = b.w;
@@ -247,16 +253,16 @@ __device__ __forceinline__ Pose load_pose(const float4* poseA, const float4* pos
 }
 
 constexpr int QCAP = 192;   // per-warp queue: candidate pairs, then static participants (0..127) + undecided segments (128..191)
-constexpr int POS_EXT_PER_WARP = 704;   // circularly extended x / y arrays: (32 / G) x (1.5 MP + 8) <= 448 floats per warp
+constexpr int POS_EXT_PER_WARP = 768;   // circularly extended x / y arrays: (32 / G) x EXT floats per warp, EXT = 1.5 MP + 16 rounded up to 4
 
 // Exact test of one candidate pair (tile indices ti, tj of the same scenario); a hit is recorded for both
 // ends as the minimum partner index (scenario-local), which is what "first hit in list order" means.
-__device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, const float4* poseA, const float4* poseB, int* hitmin) {
-  const Pose a = load_pose(poseA, poseB, ti), b = load_pose(poseA, poseB, tj);
+__device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, int psh, const float4* poseA, const float4* poseB, int* hitmin) {
+  const Pose a = load_pose(poseA, poseB, ti, psh), b = load_pose(poseA, poseB, tj, psh);
   if (pair_hit(a, b)) {
     const int mask = (1 << mp_shift) - 1;
-    atomicMin(&hitmin[ti], tj & mask);
-    atomicMin(&hitmin[tj], ti & mask);
+    atomicMin(&hitmin[pslot(ti, psh)], tj & mask);
+    atomicMin(&hitmin[pslot(tj, psh)], ti & mask);
   }
 }
 
@@ -336,15 +342,16 @@ __device__ __forceinline__ void pair_enqueue_bits(unsigned bits, int u_base, int
 template <int PPL>
 __device__ __noinline__ void pair_exhaustive(int t0, int tb, int m0, int M, int mp_shift, float rb_max, const float4* poseA,
                                              const float4* poseB, int* hitmin) {
+  constexpr int psh = PPL == 4 ? 2 : 1;
   for (int i = 0; i < PPL; ++i) {
     if (m0 + i >= M) break;
-    const float4 a = poseA[t0 + i];
+    const float4 a = poseA[pslot(t0 + i, psh)];
     if (!(a.x == a.x)) continue;
     const float rr = a.z + rb_max;
     for (int j = m0 + i + 1; j < M; ++j) {
-      const float4 b = poseA[tb + j];
+      const float4 b = poseA[pslot(tb + j, psh)];
       const float dx = b.x - a.x, dy = b.y - a.y;
-      if (fmaf(dx, dx, dy * dy) <= fmaf(rr * rr, 1.00001f, 1e-12f)) pair_resolve(t0 + i, tb + j, mp_shift, poseA, poseB, hitmin);
+      if (fmaf(dx, dx, dy * dy) <= fmaf(rr * rr, 1.00001f, 1e-12f)) pair_resolve(t0 + i, tb + j, mp_shift, psh, poseA, poseB, hitmin);
     }
   }
 }
@@ -425,30 +432,33 @@ __device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lan
     if (near) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)(t0 + i);
     base += __popc(m);
   }
+  constexpr int psh = PPL == 4 ? 2 : 1;
   __syncwarp();
   for (int k = lane; k < base; k += 32) {
     const int ti = (int)queue[k];
-    const Pose a = load_pose(poseA, poseB, ti);
-    const int best = static_walk(ti, a, poseA[ti].z, mh, seg, cell_start, items, queue, qcount);
-    segmin[ti] = best;   // one lane per participant: plain store (-2 = needs the exact walk)
+    const Pose a = load_pose(poseA, poseB, ti, psh);
+    const int best = static_walk(ti, a, poseA[pslot(ti, psh)].z, mh, seg, cell_start, items, queue, qcount);
+    segmin[pslot(ti, psh)] = best;   // one lane per participant: plain store (-2 = needs the exact walk)
   }
   __syncwarp();
   const int n_x = min(*qcount, QCAP - QX0);
   for (int k = lane; k < n_x; k += 32) {   // undecided (participant, segment) pairs: exact test
     const unsigned e = queue[QX0 + k];
     const int ti = (int)(e >> 16), sidx = (int)(e & 0xffffu);
-    if (segmin[ti] != -2 && sidx < segmin[ti] && seg_exact(load_pose(poseA, poseB, ti), seg[sidx])) atomicMin(&segmin[ti], sidx);
+    int* sm = &segmin[pslot(ti, psh)];
+    if (*sm != -2 && sidx < *sm && seg_exact(load_pose(poseA, poseB, ti, psh), seg[sidx])) atomicMin(sm, sidx);
   }
   for (int k = lane; k < base; k += 32) {   // exact-queue overflow (pathological): redo those participants out of line
     const int ti = (int)queue[k];
-    if (segmin[ti] == -2) segmin[ti] = static_walk_exact(load_pose(poseA, poseB, ti), poseA[ti].z, mh, seg, cell_start, items);
+    int* sm = &segmin[pslot(ti, psh)];
+    if (*sm == -2) *sm = static_walk_exact(load_pose(poseA, poseB, ti, psh), poseA[pslot(ti, psh)].z, mh, seg, cell_start, items);
   }
   __syncwarp();
 }
 
-__device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, int idx, float xmin, float xmax, float ymin,
+__device__ __noinline__ bool oob_slow(const float4* poseA, const float4* poseB, int idx, int psh, float xmin, float xmax, float ymin,
                                       float ymax) {
-  const Pose a = load_pose(poseA, poseB, idx);
+  const Pose a = load_pose(poseA, poseB, idx, psh);
   int r = out_of_bound_f32(a.x, a.y, a.c, a.s, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax);
   if (r < 0) r = out_of_bound_f64(a.x, a.y, a.h, a.l, a.w, a.w < 0.0f, xmin, xmax, ymin, ymax) ? 1 : 0;
   return r != 0;
@@ -558,11 +568,14 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     const long long idx0 = n * M + m0;
 
 #if defined(T2D_DEBUG_CLOCK)   // phase time stamps: measurement builds only (profiles/phase_clocks.py)
-    #define T2D_STAMP(k) do { if (A.dbg_clock && lane == 0) A.dbg_clock[(long long)tile * 10 + (k)] = clock64(); } while (0)
+    // `dep`: a late result of the phase that ends here.  The (never taken) branch on it cannot be resolved before the value
+    // has arrived, so the stamp charges a phase with the latency it creates instead of leaking it into the next one.
+    #define T2D_STAMP(k, dep) do { if (A.dbg_clock) { if (__float_as_int((float)(dep)) == 0x7fbfffff) asm volatile("trap;"); \
+      if (lane == 0) A.dbg_clock[(long long)tile * 10 + (k)] = clock64(); } } while (0)
 #else
-    #define T2D_STAMP(k) do { } while (0)
+    #define T2D_STAMP(k, dep) do { } while (0)
 #endif
-    T2D_STAMP(0);
+    T2D_STAMP(0, 0.0f);
     // ------------------------------------------------------------------ load
     // (the step counter is only needed by the status section: fetched here so that its latency is long gone by then)
     const int cnt_in = (A.do_physics && gl == 0 && scn_ok) ? A.step_count[n] : 0;
@@ -626,29 +639,31 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       mbar_wait(s_bar, 0);
       staged = true;
     }
-    if (A.cfg_flags & T2D_CFG_STEER_FIRST) {
-#pragma unroll
-      for (int i = 0; i < PPL; ++i) {
-        const Params& p = s_table[tidv[i] < A.n_types ? tidv[i] : 0];
-        if (p.model <= MODEL_DYNAMICS || p.model == MODEL_DRIFT) { float t = a0[i]; a0[i] = a1[i]; a1[i] = t; }
-      }
-    }
-
-    T2D_STAMP(1);
-    // ------------------------------------------------------------------ physics
+    // the participant's type row; its third 16-byte group holds the collision shape and the model / shape ids
+    constexpr int psh = PPL == 4 ? 2 : 1;
     float ch[PPL], sh[PPL];
     bool active[PPL], kin[PPL];
     const Params* pp[PPL];
+    int model[PPL];
     bool lane_all_kin = true, lane_any_kin = false;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
       active[i] = tidv[i] < A.n_types;
       pp[i] = &s_table[active[i] ? tidv[i] : 0];
-      kin[i] = active[i] && (pp[i]->model == MODEL_KINEMATICS);
+      model[i] = pp[i]->model_shape & 0xff;
+      kin[i] = active[i] && (model[i] == MODEL_KINEMATICS);
       lane_all_kin = lane_all_kin && kin[i];
       lane_any_kin = lane_any_kin || kin[i];
       ch[i] = 1.0f; sh[i] = 0.0f;
     }
+    if (A.cfg_flags & T2D_CFG_STEER_FIRST) {
+#pragma unroll
+      for (int i = 0; i < PPL; ++i)
+        if (model[i] <= MODEL_DYNAMICS || model[i] == MODEL_DRIFT) { float t = a0[i]; a0[i] = a1[i]; a1[i] = t; }
+    }
+
+    T2D_STAMP(1, sx[0] + sy[PPL - 1] + shd[0] + sv[PPL - 1] + a0[0] + a1[PPL - 1] + (float)tidv[0]);
+    // ------------------------------------------------------------------ physics
     if (A.do_physics) {
       // Kinematic participants of the whole warp advance together in the packed 4-chain loop; slots holding another
       // model (or nothing) ride along on a neutral row (zero speed / action, unbounded ranges) and are discarded.
@@ -715,26 +730,39 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       for (int i = 0; i < PPL; ++i) sincos_fast(shd[i], &sh[i], &ch[i]);
     }
 
-    T2D_STAMP(2);
+    T2D_STAMP(2, sx[0] + sy[PPL - 1] + ch[0] + sh[PPL - 1] + svx[PPL - 1]);
     // ------------------------------------------------------------------ poses -> shared
     // Only (x, y, bounding radius) stay in registers; the full pose lives in the warp's smem tile.
     float px[PPL], py[PPL], rb[PPL];
     unsigned solid_bits = 0;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
-      const Params& p = *pp[i];
-      const bool sol = active[i] && p.shape != SHAPE_NONE;
-      const bool circle = p.shape == SHAPE_CIRCLE;
+      const Vec4 g2 = params_group(pp[i], 2);             // (pose_l, pose_w, rbound, model | shape << 8): one 128-bit load
+      const bool sol = active[i] && (__float_as_int(g2.w) >> 8) != SHAPE_NONE;
       solid_bits |= sol ? (1u << i) : 0u;
-      // bounding radius, rounded up so the broadphase is conservative
-      rb[i] = p.rbound;
+      rb[i] = g2.z;                                       // bounding radius, rounded up so the broadphase is conservative
       px[i] = sol ? sx[i] : __int_as_float(0x7fc00000);   // NaN: a non-solid slot never passes a distance test
       py[i] = sy[i];
-      poseA[t0 + i] = make_float4(px[i], py[i], rb[i], shd[i]);
-      poseB[t0 + i] = make_float4(ch[i], sh[i], circle ? p.radius : p.half_len, circle ? -1.0f : p.half_wid);
-      hitmin[t0 + i] = 0x7fffffff;
-      if (m0 + i < M)
-        for (int k = m0 + i; k < EXT; k += M) { posx[k] = px[i]; posy[k] = py[i]; }
+      // (lane-minor layout, see pslot: these stores are conflict-free)
+      poseA[i * 32 + lane] = make_float4(px[i], py[i], rb[i], shd[i]);
+      poseB[i * 32 + lane] = make_float4(ch[i], sh[i], g2.x, g2.y);
+      hitmin[i * 32 + lane] = 0x7fffffff;
+    }
+    // circularly extended positions: slot k holds participant k mod M, i.e. this lane's PPL participants go to
+    // m0 .. m0 + PPL - 1 and to the copies M and 2 M further on that still fit
+    if (m0 < M) {
+      if (nvalid == PPL && (M & (PPL - 1)) == 0) {   // whole, aligned groups: one vector store per copy
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int k = m0 + c * M;
+          if (k < EXT) { st_vec<float, PPL>(posx + k, px); st_vec<float, PPL>(posy + k, py); }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PPL; ++i)
+          if (m0 + i < M)
+            for (int k = m0 + i; k < EXT; k += M) { posx[k] = px[i]; posy[k] = py[i]; }
+      }
     }
     if (lane == 0) *qcount = 0;
     __syncwarp();
@@ -746,7 +774,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     for (int i = 0; i < PPL; ++i)
       near_q[i] = (A.map_blob != nullptr && ((solid_bits >> i) & 1u)) ? near_fetch(px[i], py[i], rb[i], A.mh, A.map_fine) : 255u;
 
-    T2D_STAMP(3);
+    T2D_STAMP(3, 0.0f);
     // ------------------------------------------------------------------ dynamic collision
     // Every unordered pair once: participant i tests partners (i+1 .. i+M/2) mod M.  A lane walks the
     // partners of its PPL participants together (one 128-bit pose load per partner, PPL distance tests);
@@ -773,10 +801,24 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       const int n_words = Mh > 0 ? (((Mh + PPL + 1) >> 1) + IPW - 1) / IPW : 0;
       const float2* bx = reinterpret_cast<const float2*>(posx + m0);
       const float2* by = reinterpret_cast<const float2*>(posy + m0);
+      // one word = 2 * IPW consecutive partners: 128-bit loads when the lane's window is 16-byte aligned (PPL = 4)
+      auto load_word = [&](int uw, float2 (&X)[IPW], float2 (&Y)[IPW]) {
+        if constexpr (PPL == 4) {
+#pragma unroll
+          for (int q = 0; q < IPW / 2; ++q) {
+            const float4 xv = reinterpret_cast<const float4*>(bx)[uw * (IPW / 2) + q];
+            const float4 yv = reinterpret_cast<const float4*>(by)[uw * (IPW / 2) + q];
+            X[2 * q] = make_float2(xv.x, xv.y); X[2 * q + 1] = make_float2(xv.z, xv.w);
+            Y[2 * q] = make_float2(yv.x, yv.y); Y[2 * q + 1] = make_float2(yv.z, yv.w);
+          }
+        } else {
+#pragma unroll
+          for (int uu = 0; uu < IPW; ++uu) { X[uu] = bx[uw * IPW + uu]; Y[uu] = by[uw * IPW + uu]; }
+        }
+      };
       if (n_words > 0) {   // word 0 also meets the lane's own participants (offset <= 0): those tests are compiled out
         float2 X[IPW], Y[IPW];
-#pragma unroll
-        for (int uu = 0; uu < IPW; ++uu) { X[uu] = bx[uu]; Y[uu] = by[uu]; }
+        load_word(0, X, Y);
         if (pair_word_min<PPL, true>(X, Y, nx2, ny2, nthr2) <= 0.0f) {
           const unsigned bits = pair_word_bits<PPL, true>(X, Y, nx2, ny2, nthr2);
           if (bits) pair_enqueue_bits<PPL>(bits, 0, t0, tb, m0, M, Mh, queue, qcount);
@@ -784,24 +826,20 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       }
       for (int uw = 1; uw < n_words; ++uw) {
         float2 X[IPW], Y[IPW];
-#pragma unroll
-        for (int uu = 0; uu < IPW; ++uu) {
-          X[uu] = bx[uw * IPW + uu];
-          Y[uu] = by[uw * IPW + uu];
-        }
+        load_word(uw, X, Y);
         if (pair_word_min<PPL, false>(X, Y, nx2, ny2, nthr2) <= 0.0f) {
           const unsigned bits = pair_word_bits<PPL, false>(X, Y, nx2, ny2, nthr2);
           if (bits) pair_enqueue_bits<PPL>(bits, uw * IPW, t0, tb, m0, M, Mh, queue, qcount);
         }
       }
       __syncwarp();
-      T2D_STAMP(4);
+      T2D_STAMP(4, *qcount);
       // narrowphase: the queued candidate pairs, one per lane (or the exhaustive pass if the queue overflowed)
       const int n_q = *qcount;
       if (n_q <= QCAP) {
         for (int k = lane; k < n_q; k += 32) {
           const unsigned e = queue[k];
-          pair_resolve((int)(e >> 16), (int)(e & 0xffffu), mp_shift, poseA, poseB, hitmin);
+          pair_resolve((int)(e >> 16), (int)(e & 0xffffu), mp_shift, psh, poseA, poseB, hitmin);
         }
       } else {
         pair_exhaustive<PPL>(t0, tb, m0, M, mp_shift, A.rb_max, poseA, poseB, hitmin);
@@ -809,15 +847,15 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
-        const int h = hitmin[t0 + i];
+        const int h = hitmin[i * 32 + lane];
         hit[i] = (h == 0x7fffffff) ? -1 : h;
-        hitmin[t0 + i] = 0x7fffffff;   // reused below as the per-participant first-hit segment
+        hitmin[i * 32 + lane] = 0x7fffffff;   // reused below as the per-participant first-hit segment
       }
       if (lane == 0) *qcount = 0;
       __syncwarp();
     }
 
-    T2D_STAMP(5);
+    T2D_STAMP(5, hit[0] + hit[PPL - 1]);
     // ------------------------------------------------------------------ static collision
     int hseg[PPL];
 #pragma unroll
@@ -838,13 +876,13 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
                             reinterpret_cast<const uint16_t*>(A.map_blob + A.mh.off_items), poseA, poseB, hitmin, queue, qcount);
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          const int h = hitmin[t0 + i];
+          const int h = hitmin[i * 32 + lane];
           hseg[i] = (h == 0x7fffffff) ? -1 : h;
         }
       }
     }
 
-    T2D_STAMP(6);
+    T2D_STAMP(6, hseg[0] + hseg[PPL - 1]);
     // ------------------------------------------------------------------ out of bound + flags
     uint8_t fl[PPL];
 #pragma unroll
@@ -856,7 +894,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
         // the bounding circle well inside the box: inside for sure (the common case)
         const float r = rb[i] * 1.0001f + 1e-3f;
         const bool clear_in = (px[i] - A.bxmin > r) && (A.bxmax - px[i] > r) && (py[i] - A.bymin > r) && (A.bymax - py[i] > r);
-        if (!clear_in && oob_slow(poseA, poseB, t0 + i, A.bxmin, A.bxmax, A.bymin, A.bymax)) f |= T2D_F_OUTBOUND;
+        if (!clear_in && oob_slow(poseA, poseB, t0 + i, psh, A.bxmin, A.bxmax, A.bymin, A.bymax)) f |= T2D_F_OUTBOUND;
       }
       fl[i] = f;
     }
@@ -895,7 +933,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
         uint8_t st = T2D_STATUS_NORMAL;
         unsigned goal = 0;
         if (A.goal_target != nullptr) {   // the ego is participant 0 = this lane's first slot
-          const float4 ea = poseA[t0], eb = poseB[t0];
+          const float4 ea = poseA[pslot(t0, psh)], eb = poseB[pslot(t0, psh)];
           if (ea.x == ea.x && eb.w >= 0.0f) goal = ego_goal_events(A, n, ea.x, ea.y, ea.w, eb.z, eb.w);
         }
         if (goal & 1u) st = T2D_STATUS_COMPLETED;                    // parking.py:387-390 (lowest priority)
@@ -908,7 +946,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
         if (A.done) A.done[n] = st != T2D_STATUS_NORMAL;             // parking.py:243-248
       }
     }
-    T2D_STAMP(7);
+    T2D_STAMP(7, fl[0] + fl[PPL - 1]);
 #if defined(T2D_DEBUG_CLOCK)
     if (A.dbg_clock && lane == 0) {
       unsigned smid;
@@ -959,7 +997,7 @@ __global__ void t2d_reset_kernel(const __grid_constant__ ResetArgs A) {
         wf = A.pool_wf[s]; wr = A.pool_wr[s];
       } else {
         const int tid = A.type_id[i];
-        if (tid < A.n_types && A.table[tid].model == MODEL_DRIFT) wf = wr = A.pv[s] / A.table[tid].wheel_radius;   // zero slip
+        if (tid < A.n_types && A.table[tid].model() == MODEL_DRIFT) wf = wr = A.pv[s] / A.table[tid].wheel_radius;   // zero slip
       }
       A.wheel_f[i] = wf; A.wheel_r[i] = wr;
     }
@@ -1049,7 +1087,7 @@ __global__ void __launch_bounds__(128) t2d_drift_kernel(const __grid_constant__ 
     const int tid = A.type_id[i];
     if (tid >= A.n_types) continue;
     const Params& p = A.table[tid];
-    if (p.model != MODEL_DRIFT) continue;
+    if (p.model() != MODEL_DRIFT) continue;
     OneIO io;
     io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = 0.0f; io.vy = 0.0f;
     float2 act = reinterpret_cast<const float2*>(A.action)[i];
@@ -1077,7 +1115,7 @@ struct PhysArgs {
 
 __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant__ PhysArgs A) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (long long)gridDim.x * blockDim.x) {
-    if (A.p.model == MODEL_KINEMATICS) {
+    if (A.p.model() == MODEL_KINEMATICS) {
       KinIO<1> io;
       io.x[0] = A.x[i]; io.y[0] = A.y[i]; io.h[0] = A.h[i]; io.v[0] = A.v[i];
       io.acc[0] = A.action[2 * i]; io.steer[0] = A.action[2 * i + 1];
@@ -1090,7 +1128,7 @@ __global__ void __launch_bounds__(256) t2d_physics_kernel(const __grid_constant_
       io.x = A.x[i]; io.y = A.y[i]; io.h = A.h[i]; io.v = A.v[i]; io.vx = A.vx[i]; io.vy = A.vy[i];
       io.a0 = A.action[2 * i]; io.a1 = A.action[2 * i + 1];
       io.ch = 1.0f; io.sh = 0.0f;
-      if (A.p.model == MODEL_DRIFT) {
+      if (A.p.model() == MODEL_DRIFT) {
         io.w0 = A.wheel_f[i]; io.w1 = A.wheel_r[i];
         drift_step(io, A.p, A.n_steps, A.dt_d, A.dt_rem_d);
         A.wheel_f[i] = io.w0; A.wheel_r[i] = io.w1;
@@ -1178,7 +1216,7 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __
       if (r < part_rounds) {
         const int j = 1 + r * 32 + lane;
         const int tj = j < A.M ? (int)A.type_id[base + j] : 255;
-        if (tj < A.n_types && A.table[tj].shape == SHAPE_OBB) {
+        if (tj < A.n_types && A.table[tj].shape() == SHAPE_OBB) {
           const Params& pj = A.table[tj];
           const double xj = A.x[base + j], yj = A.y[base + j];
           const double reach = R + (double)pj.rbound * 1.000001 + 1e-6;
@@ -1482,9 +1520,9 @@ __global__ void __launch_bounds__(128) t2d_control_kernel(const __grid_constant_
         ctl[j] = true;
       }
       // |a| the physics will apply: single_track_kinematics.py:192 clips to the accel range; point_mass.py takes (ax, ay) as is
-      if (tp.model <= T2D_MODEL_DYNAMICS || tp.model == T2D_MODEL_DRIFT)
+      if (tp.model() <= T2D_MODEL_DYNAMICS || tp.model() == T2D_MODEL_DRIFT)
         mag[j] = fabsf(clampf(A.steer_first ? out[j].y : out[j].x, tp.accel_lo, tp.accel_hi));
-      else if (tp.model <= T2D_MODEL_POINTMASS_EULER)
+      else if (tp.model() <= T2D_MODEL_POINTMASS_EULER)
         mag[j] = (float)hypot((double)out[j].x, (double)out[j].y);
     }
     __syncwarp();
@@ -1676,7 +1714,6 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   if (!c || !table) return fail(T2D_E_INVALID, "ctx/table is NULL");
   if (n_types <= 0 || n_types > T2D_MAX_TYPES) return fail(T2D_E_INVALID, "n_types must be in 1..64");
   static_assert(sizeof(t2d_type_params) == sizeof(AbiParams), "type table layout");
-  static_assert(sizeof(Params) == 112, "device type row");
   c->has_pointmass = false;
   bool has_drift = false;
   float rb_max = 0.0f;
@@ -1974,7 +2011,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
     const int MP = c->G * c->ppl;
     A.mp_shift = 0;
     while ((1 << A.mp_shift) < MP) ++A.mp_shift;
-    A.ext = (3 * MP) / 2 + 16;
+    A.ext = ((3 * MP) / 2 + 16 + 3) & ~3;   // a multiple of 4 floats: every scenario's window starts 16-byte aligned
   }
   const int smem = A.off_bar + 16;
   if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");

@@ -62,24 +62,50 @@ struct AbiParams {
   float wheel_radius, T_sb, T_se, I_yw;   // SingleTrackDrift only
 };
 
-// The row the kernels read: the ABI row plus constants derived once on the host (28 words = 112 B).
-struct Params : AbiParams {
-  float inv_L;        // 1 / (lf + lr)
-  float lr_over_L;    // lr / (lf + lr)
-  float rbound;       // bounding-circle radius of the collision shape, rounded up
-  float pad0, pad1;
+// The row the kernels read (28 words = 112 B): the ABI values regrouped so that everything a kinematic participant
+// needs sits in THREE 16-byte groups (one 128-bit shared-memory load each instead of a dozen scalar ones; with the
+// 112-byte row stride eight consecutive rows land on distinct bank groups), plus constants derived once on the host.
+struct alignas(16) Vec4 { float x, y, z, w; };
+
+struct alignas(16) Params {
+  // group 0: action ranges
+  float accel_lo, accel_hi, steer_lo, steer_hi;
+  // group 1: speed range and the wheel-base constants  1 / (lf + lr), lr / (lf + lr)
+  float speed_lo, speed_hi, lr_over_L, inv_L;
+  // group 2: the collision shape as the pose tile stores it - (half_len, half_wid) of a box, (radius, -1) of a disc -
+  // its bounding-circle radius (rounded up), and model | shape << 8 as an integer
+  float pose_l, pose_w, rbound;
+  int32_t model_shape;
+  // the rest (fp64 models, controllers, lidar)
+  float half_len, half_wid, radius, lf, lr;
+  float mass, mass_height, mu, I_z, cf, cr;
+  float wheel_radius, T_sb, T_se, I_yw;
+  float pad0;
+  T2D_HD int model() const { return model_shape & 0xff; }
+  T2D_HD int shape() const { return model_shape >> 8; }
 };
+static_assert(sizeof(Params) == 112, "device type row");
 
 inline Params derive_params(const AbiParams& a) {
   Params p;
-  static_cast<AbiParams&>(p) = a;
   const float L = a.lf + a.lr;
+  p.accel_lo = a.accel_lo; p.accel_hi = a.accel_hi; p.steer_lo = a.steer_lo; p.steer_hi = a.steer_hi;
+  p.speed_lo = a.speed_lo; p.speed_hi = a.speed_hi;
   p.inv_L = 1.0f / L;
   p.lr_over_L = a.lr / L;
-  p.rbound = a.shape == 1 ? a.radius : sqrtf(a.half_len * a.half_len + a.half_wid * a.half_wid) * 1.000002f;
-  p.pad0 = p.pad1 = 0.0f;
+  p.rbound = a.shape == SHAPE_CIRCLE ? a.radius : sqrtf(a.half_len * a.half_len + a.half_wid * a.half_wid) * 1.000002f;
+  p.pose_l = a.shape == SHAPE_CIRCLE ? a.radius : a.half_len;
+  p.pose_w = a.shape == SHAPE_CIRCLE ? -1.0f : a.half_wid;
+  p.model_shape = a.model | (a.shape << 8);
+  p.half_len = a.half_len; p.half_wid = a.half_wid; p.radius = a.radius; p.lf = a.lf; p.lr = a.lr;
+  p.mass = a.mass; p.mass_height = a.mass_height; p.mu = a.mu; p.I_z = a.I_z; p.cf = a.cf; p.cr = a.cr;
+  p.wheel_radius = a.wheel_radius; p.T_sb = a.T_sb; p.T_se = a.T_se; p.I_yw = a.I_yw;
+  p.pad0 = 0.0f;
   return p;
 }
+
+// One 16-byte group of a row (group g starts at word 4 g).
+T2D_HD Vec4 params_group(const Params* p, int g) { return reinterpret_cast<const Vec4*>(p)[g]; }
 
 T2D_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // np.clip
 T2D_HD double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -224,25 +250,26 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
 #endif
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    a[i] = clampf(io.acc[i], p[i]->accel_lo, p[i]->accel_hi);       // :192
-    float d = clampf(io.steer[i], p[i]->steer_lo, p[i]->steer_hi);  // :193
+    const Vec4 g0 = params_group(p[i], 0), g1 = params_group(p[i], 1);   // (accel lo hi, steer lo hi), (speed lo hi, lr/L, 1/L)
+    a[i] = clampf(io.acc[i], g0.x, g0.y);       // :192
+    float d = clampf(io.steer[i], g0.z, g0.w);  // :193
     io.acc[i] = a[i];
     io.steer[i] = d;
     float sd, cd;
     sincos_narrow(d, &sd, &cd);
     float tan_d = sd / cd;
-    float tb = p[i]->lr_over_L * tan_d;       // tan(beta), beta = atan(lr/L tan delta)  :127  (L = lf + lr, :85)
+    float tb = g1.z * tan_d;                  // tan(beta), beta = atan(lr/L tan delta)  :127  (L = lf + lr, :85)
     float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
     float sb = tb * cb;                          // sin(beta)
-    k[i] = tan_d * cb * p[i]->inv_L;             // dphi = v * k                           :141
+    k[i] = tan_d * cb * g1.w;                    // dphi = v * k                           :141
     kdt[i] = k[i] * dt;
     adt[i] = a[i] * dt;
     float sp, cp;
     sincos_fast(io.h[i], &sp, &cp);
     c[i] = cp * cb - sp * sb;                    // cos(phi + beta)
     s[i] = sp * cb + cp * sb;                    // sin(phi + beta)
-    vlo[i] = p[i]->speed_lo;
-    vhi[i] = p[i]->speed_hi;
+    vlo[i] = g1.x;
+    vhi[i] = g1.y;
     const float w1u = fmaf(a[i], dt, io.v[i]);
     w1[i] = clampf(w1u, vlo[i], vhi[i]);
     const float wlu = fmaf((float)(n_steps - 1), adt[i], w1[i]);   // one step past the last speed the loop uses

@@ -17,7 +17,7 @@ void hs_physics(int n, const AbiParams* atab, const int32_t* type_id, int n_step
                 float* x, float* y, float* h, float* v, float* vx, float* vy, const float* action, float* applied) {
   for (int i = 0; i < n; ++i) {
     const Params p = derive_params(atab[type_id[i]]);
-    if (p.model == MODEL_KINEMATICS) {
+    if (p.model() == MODEL_KINEMATICS) {
       KinIO<1> io;
       io.x[0] = x[i]; io.y[0] = y[i]; io.h[0] = h[i]; io.v[0] = v[i];
       io.acc[0] = action[2 * i]; io.steer[0] = action[2 * i + 1];
@@ -29,9 +29,9 @@ void hs_physics(int n, const AbiParams* atab, const int32_t* type_id, int n_step
       OneIO io;
       io.x = x[i]; io.y = y[i]; io.h = h[i]; io.v = v[i]; io.vx = vx[i]; io.vy = vy[i];
       io.a0 = action[2 * i]; io.a1 = action[2 * i + 1]; io.ch = 1.0f; io.sh = 0.0f;
-      if (p.model == MODEL_DYNAMICS) dynamics_step(io, p, n_steps, dt);
-      else if (p.model == MODEL_POINTMASS_NEWTON) pointmass_newton_step(io, p, interval);
-      else if (p.model == MODEL_POINTMASS_EULER) pointmass_euler_step(io, p, n_steps, dt, dt_rem);
+      if (p.model() == MODEL_DYNAMICS) dynamics_step(io, p, n_steps, dt);
+      else if (p.model() == MODEL_POINTMASS_NEWTON) pointmass_newton_step(io, p, interval);
+      else if (p.model() == MODEL_POINTMASS_EULER) pointmass_euler_step(io, p, n_steps, dt, dt_rem);
       x[i] = io.x; y[i] = io.y; h[i] = io.h; v[i] = io.v; vx[i] = io.vx; vy[i] = io.vy;
       applied[2 * i] = io.a0; applied[2 * i + 1] = io.a1;
     }
