@@ -207,16 +207,24 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
 // near_fetch returns the quantised clearance under the participant (0 = treat as near: outside the grid but within
 // reach of it; 255 = far), near_decide compares it with the bounding radius.
 __device__ __forceinline__ unsigned near_fetch(const float ax, const float ay, const float rbound, const MapHeader& mh, const uint8_t* fine) {
+  // branch-free (four of these run side by side per lane): the byte under the participant is fetched from a clamped,
+  // always valid address and replaced afterwards when the position lies outside the grid.  The cell indices come
+  // from the round-to-nearest magic number (rint(f - 1/2) = floor(f) up to a cell boundary, where either neighbour's
+  // clearance is a valid lower bound) instead of float -> int conversions on the XU pipe.
   const float r = rbound * 1.0001f + 1e-3f;
   const float fx = (ax - mh.x0) * mh.inv_cell, fy = (ay - mh.y0) * mh.inv_cell;
-  const int gx = mh.gx, gy = mh.gy;
-  if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)gx && fy < (float)gy)) {
-    const float ox = fmaxf(fmaxf(-fx, fx - (float)gx), 0.0f), oy = fmaxf(fmaxf(-fy, fy - (float)gy), 0.0f);
-    return fmaxf(ox, oy) * mh.cell <= r ? 0u : 255u;   // (NaN position: 255, never near)
-  }
-  const int k = mh.fine;
-  const int ix = min((int)(fx * (float)k), gx * k - 1), iy = min((int)(fy * (float)k), gy * k - 1);
-  return (unsigned)__ldg(fine + (size_t)iy * (gx * k) + ix);
+  const float gxf = (float)mh.gx, gyf = (float)mh.gy;
+  const bool inside = fx >= 0.0f && fy >= 0.0f && fx < gxf && fy < gyf;
+  const float kf = (float)mh.fine;
+  const int nx = mh.gx * mh.fine, ny = mh.gy * mh.fine;
+  const float ux = fmaf(inside ? fx : 0.0f, kf, -0.5f), uy = fmaf(inside ? fy : 0.0f, kf, -0.5f);
+  int ix = __float_as_int(ux + RINT_MAGIC) - 0x4B400000, iy = __float_as_int(uy + RINT_MAGIC) - 0x4B400000;
+  ix = min(max(ix, 0), nx - 1); iy = min(max(iy, 0), ny - 1);
+  const unsigned q = (unsigned)__ldg(fine + (size_t)iy * nx + ix);
+  // outside the grid: reachable only within r of its box (NaN position: 255, never near)
+  const float ox = fmaxf(fmaxf(-fx, fx - gxf), 0.0f), oy = fmaxf(fmaxf(-fy, fy - gyf), 0.0f);
+  const unsigned q_out = fmaxf(ox, oy) * mh.cell <= r ? 0u : 255u;
+  return inside ? q : q_out;
 }
 __device__ __forceinline__ bool near_decide(unsigned q, const float rbound) {
   return (float)q * CLEAR_QUANT <= rbound * 1.0001f + 1e-3f;
@@ -885,18 +893,22 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     T2D_STAMP(6, hseg[0] + hseg[PPL - 1]);
     // ------------------------------------------------------------------ out of bound + flags
     uint8_t fl[PPL];
+    unsigned oob_check = 0;   // participants whose bounding circle is not well inside the box (rare): settled below, once
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
       uint8_t f = 0;
       if (hit[i] >= 0) f |= T2D_F_DYNAMIC;
       if (hseg[i] >= 0) f |= T2D_F_STATIC;
-      if (A.has_bounds && ((solid_bits >> i) & 1u)) {
-        // the bounding circle well inside the box: inside for sure (the common case)
-        const float r = rb[i] * 1.0001f + 1e-3f;
-        const bool clear_in = (px[i] - A.bxmin > r) && (A.bxmax - px[i] > r) && (py[i] - A.bymin > r) && (A.bymax - py[i] > r);
-        if (!clear_in && oob_slow(poseA, poseB, t0 + i, psh, A.bxmin, A.bxmax, A.bymin, A.bymax)) f |= T2D_F_OUTBOUND;
-      }
+      // the bounding circle well inside the box: inside for sure (the common case)
+      const float r = rb[i] * 1.0001f + 1e-3f;
+      const bool clear_in = (px[i] - A.bxmin > r) && (A.bxmax - px[i] > r) && (py[i] - A.bymin > r) && (A.bymax - py[i] > r);
+      if (A.has_bounds && ((solid_bits >> i) & 1u) && !clear_in) oob_check |= 1u << i;
       fl[i] = f;
+    }
+    if (oob_check) {
+#pragma unroll
+      for (int i = 0; i < PPL; ++i)
+        if (((oob_check >> i) & 1u) && oob_slow(poseA, poseB, t0 + i, psh, A.bxmin, A.bxmax, A.bymin, A.bymax)) fl[i] |= T2D_F_OUTBOUND;
     }
     if (nvalid == PPL && A.vec_ok) {
       int16_t h16[PPL], s16[PPL];

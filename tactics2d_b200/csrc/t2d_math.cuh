@@ -19,6 +19,7 @@
 #pragma once
 
 #include <math.h>
+#include <string.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -110,9 +111,31 @@ T2D_HD Vec4 params_group(const Params* p, int g) { return reinterpret_cast<const
 T2D_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // np.clip
 T2D_HD double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-// np.mod(phi, 2*pi) for an fp32 angle: result in [0, 2*pi) (Cody-Waite two-term reduction).
+// Bits of a float (device: a register move; host: memcpy).
+T2D_HD int float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i;
+  memcpy(&i, &f, sizeof(i));
+  return i;
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define T2D_FDIV(a, b) __fdividef((a), (b))   // reciprocal + multiply (2 ulp), no slow-path branch
+#else
+#define T2D_FDIV(a, b) ((a) / (b))
+#endif
+
+// Round-to-nearest-integer without the conversion unit: adding 1.5 * 2^23 leaves rint(u) in the low mantissa bits
+// (|u| < 2^22).  On sm_100a FRND / F2I run on the quarter-rate XU pipe, the busiest pipe of the tick before this.
+constexpr float RINT_MAGIC = 12582912.0f;
+
+// np.mod(phi, 2*pi) for an fp32 angle: result in [0, 2*pi) (Cody-Waite two-term reduction).  q = rint(phi / 2 pi - 1/2)
+// is floor(phi / 2 pi) or its neighbour (at ties); the two corrections below absorb either.
 T2D_HD float wrap_two_pi(float phi) {
-  float q = floorf(phi * INV_TWO_PI);
+  const float q = (fmaf(phi, INV_TWO_PI, -0.5f) + RINT_MAGIC) - RINT_MAGIC;
   float r = fmaf(-q, TWO_PI_HI, phi);
   r = fmaf(-q, TWO_PI_LO, r);
   if (r < 0.0f) r += TWO_PI_HI;
@@ -141,37 +164,33 @@ T2D_HD void sincos_poly(float r, float& s, float& c) {
            fmaf(-0.5f, z, 1.0f));
 }
 
+// The branch-free part: correct for |x| <= 512 (NaN / inf give NaN).  Callers that cannot rule out larger arguments
+// check that themselves, ONCE for a whole group of evaluations, so that the evaluations of independent participants
+// stay in one basic block and interleave (a slow-path CALL after every evaluation serialises them).
+T2D_HD void sincos_core(float x, float& so, float& co) {
+  const float t = fmaf(x, 0.636619772f, RINT_MAGIC);   // the quadrant k = rint(x * 2 / pi) sits in t's low mantissa bits
+  const float k = t - RINT_MAGIC;
+  float r = fmaf(-k, 1.570556640625f, x);
+  r = fmaf(-k, 2.396702766418457e-4f, r);
+  r = fmaf(-k, 1.5893254712295857e-8f, r);
+  float s, c;
+  sincos_poly(r, s, c);
+  const int q = float_bits(t);
+  const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+  so = (q & 2) ? -a : a;
+  co = ((q + 1) & 2) ? -b : b;
+}
+
 T2D_HD void sincos_fast(float x, float* sn, float* cs) {
   float so, co;
   if (!(fabsf(x) <= 512.0f)) {
     const SinCos r = sincosf_slow(x);
     so = r.s; co = r.c;
   } else {
-    const float k = rintf(x * 0.636619772f);
-    float r = fmaf(-k, 1.570556640625f, x);
-    r = fmaf(-k, 2.396702766418457e-4f, r);
-    r = fmaf(-k, 1.5893254712295857e-8f, r);
-    float s, c;
-    sincos_poly(r, s, c);
-    const int q = (int)k;
-    const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
-    so = (q & 2) ? -a : a;
-    co = ((q + 1) & 2) ? -b : b;
+    sincos_core(x, so, co);
   }
   *sn = so;
   *cs = co;
-}
-
-// sincos of an angle that is almost always inside [-pi/4, pi/4] (a clipped steering angle): there the reduction of
-// sincos_fast is the identity (k = 0), so the polynomials alone give bit-identical results.
-T2D_HD void sincos_narrow(float x, float* sn, float* cs) {
-  if (fabsf(x) <= 0.78f) {
-    float s, c;
-    sincos_poly(x, s, c);
-    *sn = s; *cs = c;
-  } else {
-    sincos_fast(x, sn, cs);
-  }
 }
 
 // Small-angle rotation, |d| <= 0.25 (Taylor: |err| < 2e-9 on cos, 1.3e-8 relative on sin).
@@ -223,7 +242,7 @@ T2D_HD void kinematics_finish(KinIO<W>& io, const Params* const (&p)[W], const f
     }
     float hn = wrap_two_pi(io.h[i] + dphi);     // np.mod(phi, 2 pi)                        :169
     float sh, ch;
-    sincos_fast(hn, &sh, &ch);
+    sincos_core(hn, sh, ch);                    // hn is in [0, 2 pi] (or NaN): no large-argument path needed
     io.x[i] = x; io.y[i] = y; io.h[i] = hn; io.v[i] = v[i];
     io.vx[i] = v[i] * ch;                        // v cos(phi), no beta                    :170
     io.vy[i] = v[i] * sh;                        //                                        :171
@@ -248,26 +267,40 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
   // below 7e-6 there), so longer ticks keep the general loop
   bool lin = n_steps >= 2 && n_steps <= 24;
 #endif
+  // Trigonometry of the steering angle and the heading first, for all W participants in one basic block; the arguments
+  // the short forms cannot take (a steering range beyond +-pi/4, a heading beyond +-512) are re-done afterwards, once.
+  float sd[W], cd[W], sp[W], cp[W];
+  bool rare = false;
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    const Vec4 g0 = params_group(p[i], 0), g1 = params_group(p[i], 1);   // (accel lo hi, steer lo hi), (speed lo hi, lr/L, 1/L)
+    const Vec4 g0 = params_group(p[i], 0);      // accel lo hi, steer lo hi
     a[i] = clampf(io.acc[i], g0.x, g0.y);       // :192
-    float d = clampf(io.steer[i], g0.z, g0.w);  // :193
+    const float d = clampf(io.steer[i], g0.z, g0.w);  // :193
     io.acc[i] = a[i];
     io.steer[i] = d;
-    float sd, cd;
-    sincos_narrow(d, &sd, &cd);
-    float tan_d = sd / cd;
-    float tb = g1.z * tan_d;                  // tan(beta), beta = atan(lr/L tan delta)  :127  (L = lf + lr, :85)
-    float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
-    float sb = tb * cb;                          // sin(beta)
+    sincos_poly(d, sd[i], cd[i]);               // = sincos_fast for |d| <= pi/4 (its reduction is the identity there)
+    sincos_core(io.h[i], sp[i], cp[i]);
+    rare = rare || !(fabsf(d) <= 0.78f) || !(fabsf(io.h[i]) <= 512.0f);
+  }
+  if (rare) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (!(fabsf(io.steer[i]) <= 0.78f)) sincos_fast(io.steer[i], &sd[i], &cd[i]);
+      if (!(fabsf(io.h[i]) <= 512.0f)) sincos_fast(io.h[i], &sp[i], &cp[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const Vec4 g1 = params_group(p[i], 1);      // speed lo hi, lr / L, 1 / L
+    const float tan_d = T2D_FDIV(sd[i], cd[i]);
+    const float tb = g1.z * tan_d;              // tan(beta), beta = atan(lr/L tan delta)  :127  (L = lf + lr, :85)
+    const float cb = T2D_RSQRTF(fmaf(tb, tb, 1.0f));  // cos(beta)
+    const float sb = tb * cb;                    // sin(beta)
     k[i] = tan_d * cb * g1.w;                    // dphi = v * k                           :141
     kdt[i] = k[i] * dt;
     adt[i] = a[i] * dt;
-    float sp, cp;
-    sincos_fast(io.h[i], &sp, &cp);
-    c[i] = cp * cb - sp * sb;                    // cos(phi + beta)
-    s[i] = sp * cb + cp * sb;                    // sin(phi + beta)
+    c[i] = cp[i] * cb - sp[i] * sb;              // cos(phi + beta)
+    s[i] = sp[i] * cb + cp[i] * sb;              // sin(phi + beta)
     vlo[i] = g1.x;
     vhi[i] = g1.y;
     const float w1u = fmaf(a[i], dt, io.v[i]);
