@@ -206,7 +206,8 @@ __device__ __noinline__ void other_model_step(OneIO& io, const Params& p, int n_
 // near_segments split in two so that the global byte load can be issued early and consumed late:
 // near_fetch returns the quantised clearance under the participant (0 = treat as near: outside the grid but within
 // reach of it; 255 = far), near_decide compares it with the bounding radius.
-__device__ __forceinline__ unsigned near_fetch(const float ax, const float ay, const float rbound, const MapHeader& mh, const uint8_t* fine) {
+__device__ __forceinline__ unsigned near_fetch(const float ax, const float ay, const float rbound, const MapHeader& mh, const uint8_t* fine,
+                                               unsigned& alt) {
   // branch-free (four of these run side by side per lane): the byte under the participant is fetched from a clamped,
   // always valid address and replaced afterwards when the position lies outside the grid.  The cell indices come
   // from the round-to-nearest magic number (rint(f - 1/2) = floor(f) up to a cell boundary, where either neighbour's
@@ -224,10 +225,14 @@ __device__ __forceinline__ unsigned near_fetch(const float ax, const float ay, c
   // outside the grid: reachable only within r of its box (NaN position: 255, never near)
   const float ox = fmaxf(fmaxf(-fx, fx - gxf), 0.0f), oy = fmaxf(fmaxf(-fy, fy - gyf), 0.0f);
   const unsigned q_out = fmaxf(ox, oy) * mh.cell <= r ? 0u : 255u;
-  return inside ? q : q_out;
+  // The loaded byte is NOT touched here (its first use would stall the lane on the L2 round trip): it is returned as
+  // loaded; `alt` says what to take instead - 0xffffffff: nothing (inside the grid), else the value for outside.
+  alt = inside ? 0xffffffffu : q_out;
+  return q;
 }
-__device__ __forceinline__ bool near_decide(unsigned q, const float rbound) {
-  return (float)q * CLEAR_QUANT <= rbound * 1.0001f + 1e-3f;
+__device__ __forceinline__ bool near_decide(unsigned q, unsigned alt, const float rbound) {
+  const unsigned v = alt == 0xffffffffu ? q : alt;
+  return (float)v * CLEAR_QUANT <= rbound * 1.0001f + 1e-3f;
 }
 
 __device__ __forceinline__ bool near_segments(const float ax, const float ay, const float rbound, const MapHeader& mh,
@@ -585,8 +590,6 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
 #endif
     T2D_STAMP(0, 0.0f);
     // ------------------------------------------------------------------ load
-    // (the step counter is only needed by the status section: fetched here so that its latency is long gone by then)
-    const int cnt_in = (A.do_physics && gl == 0 && scn_ok) ? A.step_count[n] : 0;
     float sx[PPL], sy[PPL], shd[PPL], sv[PPL], svx[PPL], svy[PPL], a0[PPL], a1[PPL];
     int tidv[PPL];
 #pragma unroll
@@ -774,13 +777,24 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     }
     if (lane == 0) *qcount = 0;
     __syncwarp();
+    // the step counter of the status section: fetched here - behind the state stores, so it cannot be hoisted to the top
+    // of the tile (where ptxas spilled it, stalling the warp on HBM before its state loads were even issued), and with
+    // the whole collision phase in front of its first use
+    const int cnt_in = (A.do_physics && gl == 0 && scn_ok) ? A.step_count[n] : 0;
 
     // static broadphase level 1 (clearance field: one byte per participant through L1/L2), issued here so that
     // its global-load latency hides behind the partner loop
-    unsigned near_q[PPL];
+    unsigned near_q[PPL], near_alt[PPL];
 #pragma unroll
-    for (int i = 0; i < PPL; ++i)
-      near_q[i] = (A.map_blob != nullptr && ((solid_bits >> i) & 1u)) ? near_fetch(px[i], py[i], rb[i], A.mh, A.map_fine) : 255u;
+    for (int i = 0; i < PPL; ++i) { near_q[i] = 255u; near_alt[i] = 255u; }   // 255 = far from every segment
+    if (A.map_blob != nullptr) {
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        unsigned alt;
+        near_q[i] = near_fetch(px[i], py[i], rb[i], A.mh, A.map_fine, alt);   // (a NaN position reads cell 0 and is "outside": alt = 255)
+        near_alt[i] = ((solid_bits >> i) & 1u) ? alt : 255u;
+      }
+    }
 
     T2D_STAMP(3, 0.0f);
     // ------------------------------------------------------------------ dynamic collision
@@ -872,7 +886,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       unsigned near_bits = 0;
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
-        if (((solid_bits >> i) & 1u) && near_decide(near_q[i], rb[i])) near_bits |= 1u << i;
+        if (((solid_bits >> i) & 1u) && near_decide(near_q[i], near_alt[i], rb[i])) near_bits |= 1u << i;
       if (__any_sync(0xffffffffu, near_bits != 0)) {
         if (A.map_in_smem)
           static_phase<PPL>(near_bits, t0, lane, A.mh, reinterpret_cast<const float4*>(s_map + A.mh.off_seg),
