@@ -43,16 +43,22 @@ constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host p
 constexpr int POSE_PER_WARP = 128;      // 32 lanes x 4 participants per lane (PPL, template parameter of K1: 2 or 4)
 constexpr int MAP_SMEM_LIMIT = 120 * 1024;
 
-struct MapHeader {   // 64 bytes, start of the map blob
+struct MapHeader {   // 96 bytes, start of the map blob
   int32_t n_seg, gx, gy, n_items;
   float x0, y0, inv_cell, cell;
   uint32_t off_seg, off_cell, off_items, total_bytes;
   uint32_t off_clear;   // float per cell: lower bound of the distance from any point of the cell to any segment
   int32_t fine;         // the fine clearance field has (gx * fine) x (gy * fine) cells, one byte each (global memory)
-  uint32_t pad[2];
+  // "dilated" lists: cell c lists (ascending) every segment that comes within `dil` metres of the cell's box, so that a
+  // participant whose bounding radius is <= dil finds all its candidates in the ONE cell under its centre (the grid
+  // covers the segments' bounding box grown by dil: a centre outside it cannot reach a segment)
+  uint32_t off_dcell, off_ditems;
+  float dil;
+  int32_t n_ditems;
+  uint32_t pad[6];
 };
 constexpr float CLEAR_QUANT = 0.125f;   // metres per unit of the byte-quantised fine clearance field
-static_assert(sizeof(MapHeader) == 64, "MapHeader must be 64 bytes");
+static_assert(sizeof(MapHeader) == 96, "MapHeader must be 96 bytes");
 
 struct StepArgs {
   float *x, *y, *h, *v, *vx, *vy;
@@ -376,43 +382,59 @@ __device__ __noinline__ void pair_exhaustive(int t0, int tb, int m0, int M, int 
 // marked (returns -2) for the out-of-line exact walk.
 constexpr int QX0 = 128;   // first exact-queue entry (entries below hold the compacted participant list)
 
-template <typename SegPtr, typename CellPtr, typename ItemPtr>
-__device__ __forceinline__ int static_walk(int ti, const Pose& a, float rbound, const MapHeader& mh, SegPtr seg, CellPtr cell_start,
-                                           ItemPtr items, unsigned* queue, int* qcount) {
-  const int gx = mh.gx, gy = mh.gy;
-  const float x0 = mh.x0, y0 = mh.y0, inv = mh.inv_cell;
+// The sections of a map blob (in shared or in global memory: the accessors are inlined, the address space is known).
+struct MapView {
+  const float4* seg;
+  const uint32_t* cell_start;
+  const uint16_t* items;
+  const uint32_t* dcell_start;
+  const uint16_t* ditems;
+};
+__device__ __forceinline__ MapView map_view(const unsigned char* blob, const MapHeader& mh) {
+  MapView v;
+  v.seg = reinterpret_cast<const float4*>(blob + mh.off_seg);
+  v.cell_start = reinterpret_cast<const uint32_t*>(blob + mh.off_cell);
+  v.items = reinterpret_cast<const uint16_t*>(blob + mh.off_items);
+  v.dcell_start = reinterpret_cast<const uint32_t*>(blob + mh.off_dcell);
+  v.ditems = reinterpret_cast<const uint16_t*>(blob + mh.off_ditems);
+  return v;
+}
+
+// Static level 2 for ONE participant whose reach is <= the map's dilation: ONE cell look-up (the cell under the centre)
+// and one loop over its dilated list.  Returns the lowest hit, 0x7fffffff for none, -2 when the participant needs the
+// out-of-line walk (reach beyond the dilation, or the exact queue is full).
+__device__ __forceinline__ int static_walk(int ti, const Pose& a, float rbound, const MapHeader& mh, const MapView& mv, unsigned* queue,
+                                           int* qcount) {
   const float r = rbound * 1.0001f + 1e-3f;
-  int cx0 = (int)floorf((a.x - r - x0) * inv), cx1 = (int)floorf((a.x + r - x0) * inv);
-  int cy0 = (int)floorf((a.y - r - y0) * inv), cy1 = (int)floorf((a.y + r - y0) * inv);
-  cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, gx - 1); cy1 = min(cy1, gy - 1);
+  if (!(r <= mh.dil)) return -2;
+  const float fx = (a.x - mh.x0) * mh.inv_cell, fy = (a.y - mh.y0) * mh.inv_cell;
+  if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)mh.gx && fy < (float)mh.gy)) return 0x7fffffff;   // beyond the grown box: out of reach
+  const int cx = min((int)fx, mh.gx - 1), cy = min((int)fy, mh.gy - 1);
+  const int cidx = cy * mh.gx + cx;
+  const uint32_t b = mv.dcell_start[cidx], e = mv.dcell_start[cidx + 1];
   int best = 0x7fffffff;
   bool overflow = false;
-  for (int cy = cy0; cy <= cy1; ++cy)
-    for (int cx = cx0; cx <= cx1; ++cx) {
-      const int cidx = cy * gx + cx;
-      const uint32_t b = cell_start[cidx], e = cell_start[cidx + 1];
-      for (uint32_t k = b; k < e; ++k) {
-        const int sidx = items[k];
-        if (sidx >= best) break;   // lists are ascending: nothing better left in this cell
-        const float4 sg = seg[sidx];
-        const int rr = a.w < 0.0f ? circle_segment_f32(a.x, a.y, a.l, sg.x, sg.y, sg.z, sg.w)
-                                  : obb_segment_f32(a.x, a.y, a.c, a.s, a.l, a.w, sg.x, sg.y, sg.z, sg.w);
-        if (rr > 0) {
-          best = sidx;
-        } else if (rr < 0) {
-          const int slot = atomicAdd(qcount, 1);
-          if (slot < QCAP - QX0) queue[QX0 + slot] = ((unsigned)ti << 16) | (unsigned)sidx;
-          else overflow = true;
-        }
-      }
+  for (uint32_t k = b; k < e; ++k) {
+    const int sidx = mv.ditems[k];
+    const float4 sg = mv.seg[sidx];
+    const int rr = a.w < 0.0f ? circle_segment_f32(a.x, a.y, a.l, sg.x, sg.y, sg.z, sg.w)
+                              : obb_segment_f32(a.x, a.y, a.c, a.s, a.l, a.w, sg.x, sg.y, sg.z, sg.w);
+    if (rr > 0) {
+      best = sidx;   // the list is ascending: the first hit is the lowest
+      break;
+    } else if (rr < 0) {
+      const int slot = atomicAdd(qcount, 1);
+      if (slot < QCAP - QX0) queue[QX0 + slot] = ((unsigned)ti << 16) | (unsigned)sidx;
+      else overflow = true;
     }
+  }
   return overflow ? -2 : best;
 }
 
 // Out-of-line exact walk for a participant whose undecided segments did not fit the exact queue (never on the
 // hot path): the same cells, every test through the fp32 filter + fp64 fallback.
-template <typename SegPtr, typename CellPtr, typename ItemPtr>
-__device__ __noinline__ int static_walk_exact(const Pose a, float rbound, const MapHeader mh, SegPtr seg, CellPtr cell_start, ItemPtr items) {
+__device__ __noinline__ int static_walk_exact(const Pose a, float rbound, const MapHeader mh, const float4* seg, const uint32_t* cell_start,
+                                              const uint16_t* items) {
   const float r = rbound * 1.0001f + 1e-3f;
   int cx0 = max((int)floorf((a.x - r - mh.x0) * mh.inv_cell), 0), cx1 = min((int)floorf((a.x + r - mh.x0) * mh.inv_cell), mh.gx - 1);
   int cy0 = max((int)floorf((a.y - r - mh.y0) * mh.inv_cell), 0), cy1 = min((int)floorf((a.y + r - mh.y0) * mh.inv_cell), mh.gy - 1);
@@ -433,10 +455,10 @@ __device__ __noinline__ int static_walk_exact(const Pose a, float rbound, const 
 // can reach a wall at all; (2) those participants are compacted into a list with warp ballots; (3) the list is
 // processed one participant per lane (static_walk), so the divergent cell walks of ~15 % of the participants run
 // side by side instead of one after the other; (4) the few filter-undecided segments are settled in fp64.
-template <int PPL, typename SegPtr, typename CellPtr, typename ItemPtr>
-__device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lane, const MapHeader& mh, SegPtr seg, CellPtr cell_start,
-                                             ItemPtr items, const float4* poseA, const float4* poseB, int* segmin, unsigned* queue,
-                                             int* qcount) {
+template <int PPL>
+__device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lane, const MapHeader& mh, const MapView& mv,
+                                             const float4* poseA, const float4* poseB, int* segmin, unsigned* queue, int* qcount) {
+  const float4* seg = mv.seg;
   int base = 0;
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
@@ -450,7 +472,7 @@ __device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lan
   for (int k = lane; k < base; k += 32) {
     const int ti = (int)queue[k];
     const Pose a = load_pose(poseA, poseB, ti, psh);
-    const int best = static_walk(ti, a, poseA[pslot(ti, psh)].z, mh, seg, cell_start, items, queue, qcount);
+    const int best = static_walk(ti, a, poseA[pslot(ti, psh)].z, mh, mv, queue, qcount);
     segmin[pslot(ti, psh)] = best;   // one lane per participant: plain store (-2 = needs the exact walk)
   }
   __syncwarp();
@@ -464,7 +486,7 @@ __device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lan
   for (int k = lane; k < base; k += 32) {   // exact-queue overflow (pathological): redo those participants out of line
     const int ti = (int)queue[k];
     int* sm = &segmin[pslot(ti, psh)];
-    if (*sm == -2) *sm = static_walk_exact(load_pose(poseA, poseB, ti, psh), poseA[pslot(ti, psh)].z, mh, seg, cell_start, items);
+    if (*sm == -2) *sm = static_walk_exact(load_pose(poseA, poseB, ti, psh), poseA[pslot(ti, psh)].z, mh, mv.seg, mv.cell_start, mv.items);
   }
   __syncwarp();
 }
@@ -889,13 +911,9 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
         if (((solid_bits >> i) & 1u) && near_decide(near_q[i], near_alt[i], rb[i])) near_bits |= 1u << i;
       if (__any_sync(0xffffffffu, near_bits != 0)) {
         if (A.map_in_smem)
-          static_phase<PPL>(near_bits, t0, lane, A.mh, reinterpret_cast<const float4*>(s_map + A.mh.off_seg),
-                            reinterpret_cast<const uint32_t*>(s_map + A.mh.off_cell),
-                            reinterpret_cast<const uint16_t*>(s_map + A.mh.off_items), poseA, poseB, hitmin, queue, qcount);
+          static_phase<PPL>(near_bits, t0, lane, A.mh, map_view(s_map, A.mh), poseA, poseB, hitmin, queue, qcount);
         else
-          static_phase<PPL>(near_bits, t0, lane, A.mh, reinterpret_cast<const float4*>(A.map_blob + A.mh.off_seg),
-                            reinterpret_cast<const uint32_t*>(A.map_blob + A.mh.off_cell),
-                            reinterpret_cast<const uint16_t*>(A.map_blob + A.mh.off_items), poseA, poseB, hitmin, queue, qcount);
+          static_phase<PPL>(near_bits, t0, lane, A.mh, map_view(A.map_blob, A.mh), poseA, poseB, hitmin, queue, qcount);
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
           const int h = hitmin[i * 32 + lane];
@@ -1824,55 +1842,73 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   }
   const float span = std::max(xmax - xmin, ymax - ymin);
   float cell = cell_size > 0.0f ? cell_size : 8.0f;
-  // keep the grid small enough for shared memory: at most 64 x 64 cells
-  while (span / cell > 64.0f) cell *= 2.0f;
+  // keep the grid small enough for shared memory: at most 64 x 64 cells over the box grown by one cell (the dilation)
+  while (span / cell > 62.0f) cell *= 2.0f;
+  const float dil = cell;   // reach of the dilated lists (>= the bounding radius of every template vehicle at 8 m cells)
   const float margin = 1e-3f * std::max(1.0f, std::max(std::fabs(xmin) + std::fabs(xmax), std::fabs(ymin) + std::fabs(ymax)) * 1e-3f);
-  const float x0 = xmin - margin, y0 = ymin - margin;
-  const int gx = std::max(1, (int)std::floor((xmax + margin - x0) / cell) + 1);
-  const int gy = std::max(1, (int)std::floor((ymax + margin - y0) / cell) + 1);
-  std::vector<std::vector<uint16_t>> cells((size_t)gx * gy);
+  const float x0 = xmin - dil - margin, y0 = ymin - dil - margin;
+  const int gx = std::max(1, (int)std::floor((xmax + dil + margin - x0) / cell) + 1);
+  const int gy = std::max(1, (int)std::floor((ymax + dil + margin - y0) / cell) + 1);
   const float inv = 1.0f / cell;
-  for (int i = 0; i < n_seg; ++i) {
-    const float* s = segments + 4 * i;
-    const float sx0 = std::min(s[0], s[2]) - margin, sx1 = std::max(s[0], s[2]) + margin;
-    const float sy0 = std::min(s[1], s[3]) - margin, sy1 = std::max(s[1], s[3]) + margin;
-    int cx0 = std::max(0, (int)std::floor((sx0 - x0) * inv) - 0), cx1 = std::min(gx - 1, (int)std::floor((sx1 - x0) * inv));
-    int cy0 = std::max(0, (int)std::floor((sy0 - y0) * inv) - 0), cy1 = std::min(gy - 1, (int)std::floor((sy1 - y0) * inv));
-    for (int cy = cy0; cy <= cy1; ++cy)
-      for (int cx = cx0; cx <= cx1; ++cx) {
-        // exact-enough cull: does the segment's line pass within the (grown) cell box?
-        const float bx0 = x0 + cx * cell - margin, bx1 = x0 + (cx + 1) * cell + margin;
-        const float by0 = y0 + cy * cell - margin, by1 = y0 + (cy + 1) * cell + margin;
-        const double dx = (double)s[2] - s[0], dy = (double)s[3] - s[1];
-        const double hx = 0.5 * ((double)bx1 - bx0), hy = 0.5 * ((double)by1 - by0);
-        const double mx = 0.5 * ((double)bx1 + bx0), my = 0.5 * ((double)by1 + by0);
-        const double cr = std::fabs(((double)s[0] - mx) * dy - ((double)s[1] - my) * dx);
-        if (cr > hx * std::fabs(dy) + hy * std::fabs(dx) + 1e-6 * (std::fabs(dx) + std::fabs(dy) + 1.0)) continue;
-        cells[(size_t)cy * gx + cx].push_back((uint16_t)i);
-      }
-  }
-  size_t n_items = 0;
+  // cells[c] lists (ascending) the segments that pass within `grow` of cell c's box (conservatively: the segment's line
+  // against the box grown by `grow` on every side)
+  auto bin_segments = [&](float grow) {
+    std::vector<std::vector<uint16_t>> cells((size_t)gx * gy);
+    for (int i = 0; i < n_seg; ++i) {
+      const float* s = segments + 4 * i;
+      const float g = grow + margin;
+      const float sx0 = std::min(s[0], s[2]) - g, sx1 = std::max(s[0], s[2]) + g;
+      const float sy0 = std::min(s[1], s[3]) - g, sy1 = std::max(s[1], s[3]) + g;
+      int cx0 = std::max(0, (int)std::floor((sx0 - x0) * inv)), cx1 = std::min(gx - 1, (int)std::floor((sx1 - x0) * inv));
+      int cy0 = std::max(0, (int)std::floor((sy0 - y0) * inv)), cy1 = std::min(gy - 1, (int)std::floor((sy1 - y0) * inv));
+      for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+          // exact-enough cull: does the segment's line pass within the grown cell box?
+          const float bx0 = x0 + cx * cell - g, bx1 = x0 + (cx + 1) * cell + g;
+          const float by0 = y0 + cy * cell - g, by1 = y0 + (cy + 1) * cell + g;
+          const double dx = (double)s[2] - s[0], dy = (double)s[3] - s[1];
+          const double hx = 0.5 * ((double)bx1 - bx0), hy = 0.5 * ((double)by1 - by0);
+          const double mx = 0.5 * ((double)bx1 + bx0), my = 0.5 * ((double)by1 + by0);
+          const double cr = std::fabs(((double)s[0] - mx) * dy - ((double)s[1] - my) * dx);
+          if (cr > hx * std::fabs(dy) + hy * std::fabs(dx) + 1e-6 * (std::fabs(dx) + std::fabs(dy) + 1.0)) continue;
+          cells[(size_t)cy * gx + cx].push_back((uint16_t)i);
+        }
+    }
+    return cells;
+  };
+  const std::vector<std::vector<uint16_t>> cells = bin_segments(0.0f);
+  // the dilated lists serve participants with reach r <= dil from the cell under their centre: every segment within r
+  // of the centre is within dil of that cell's box (+ a 0.1 % + 1 mm guard for the fp32 cell index)
+  const std::vector<std::vector<uint16_t>> dcells = bin_segments(dil * 1.001f + 1e-3f);
+  size_t n_items = 0, n_ditems = 0;
   for (auto& v : cells) n_items += v.size();
+  for (auto& v : dcells) n_ditems += v.size();
   MapHeader mh{};
-  mh.n_seg = n_seg; mh.gx = gx; mh.gy = gy; mh.n_items = (int)n_items;
-  mh.x0 = x0; mh.y0 = y0; mh.inv_cell = inv; mh.cell = cell;
+  mh.n_seg = n_seg; mh.gx = gx; mh.gy = gy; mh.n_items = (int)n_items; mh.n_ditems = (int)n_ditems;
+  mh.x0 = x0; mh.y0 = y0; mh.inv_cell = inv; mh.cell = cell; mh.dil = dil;
   auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
-  mh.off_seg = 64;
+  mh.off_seg = (uint32_t)up16(sizeof(MapHeader));
   mh.off_cell = (uint32_t)up16(mh.off_seg + (size_t)n_seg * 16);
   mh.off_items = (uint32_t)up16(mh.off_cell + ((size_t)gx * gy + 1) * 4);
-  mh.off_clear = (uint32_t)up16(mh.off_items + n_items * 2);
+  mh.off_dcell = (uint32_t)up16(mh.off_items + n_items * 2);
+  mh.off_ditems = (uint32_t)up16(mh.off_dcell + ((size_t)gx * gy + 1) * 4);
+  mh.off_clear = (uint32_t)up16(mh.off_ditems + n_ditems * 2);
   mh.total_bytes = (uint32_t)up16(mh.off_clear + (size_t)gx * gy * 4);
   std::vector<unsigned char> blob(mh.total_bytes, 0);
   memcpy(blob.data(), &mh, sizeof(mh));
   memcpy(blob.data() + mh.off_seg, segments, (size_t)n_seg * 16);
-  uint32_t* cs = reinterpret_cast<uint32_t*>(blob.data() + mh.off_cell);
-  uint16_t* it = reinterpret_cast<uint16_t*>(blob.data() + mh.off_items);
-  uint32_t acc = 0;
-  for (size_t ci = 0; ci < cells.size(); ++ci) {
-    cs[ci] = acc;
-    for (uint16_t s : cells[ci]) it[acc++] = s;
-  }
-  cs[cells.size()] = acc;
+  auto write_lists = [&](const std::vector<std::vector<uint16_t>>& lists, uint32_t off_start, uint32_t off_items) {
+    uint32_t* cs = reinterpret_cast<uint32_t*>(blob.data() + off_start);
+    uint16_t* it = reinterpret_cast<uint16_t*>(blob.data() + off_items);
+    uint32_t acc = 0;
+    for (size_t ci = 0; ci < lists.size(); ++ci) {
+      cs[ci] = acc;
+      for (uint16_t sg : lists[ci]) it[acc++] = sg;
+    }
+    cs[lists.size()] = acc;
+  };
+  write_lists(cells, mh.off_cell, mh.off_items);
+  write_lists(dcells, mh.off_dcell, mh.off_ditems);
   // clearance fields: lower bound of the distance from any point of a cell to the nearest segment
   // (distance from the cell centre minus the half diagonal).  Coarse (float, in the blob) and fine
   // (bytes of CLEAR_QUANT metres, 4 x 4 per coarse cell, in global memory).
