@@ -230,7 +230,13 @@ def run_ours(args):
 
     lib = _lib.load()
     K, W = args.steps, max(args.warmup, 3)
-    scene0 = make_scene(args.config, seed=1 + 1000 * rank)
+    n_cfg = args.scenarios or None
+    if args.sharded:   # the configuration's N is the whole job: every rank takes a contiguous 1 / world_size share of it
+        from tactics2d_b200.distributed import shard_range
+        total = args.scenarios or {"c2": N_SCN, "c3": 4096, "c4": 16384, "c5": 65536}[args.config]
+        lo, hi = shard_range(total, rank, world_size)
+        n_cfg = hi - lo
+    scene0 = make_scene(args.config, seed=1 + 1000 * rank, n=n_cfg)
     n, m = scene0.shape
     bytes_per_launch = n * m * BYTES_PER_PARTICIPANT + n * BYTES_PER_SCENARIO
     l2_bytes = torch.cuda.get_device_properties(device).L2_cache_size
@@ -239,7 +245,7 @@ def run_ours(args):
 
     worlds, actions, pools = [], [], []
     for r in range(R):
-        sc = scene0 if r == 0 else make_scene(args.config, seed=1 + 1000 * rank + r)
+        sc = scene0 if r == 0 else make_scene(args.config, seed=1 + 1000 * rank + r, n=n_cfg)
         w = BatchedWorld(n, m, sc.table, device=device, max_step=0)
         w.set_map(sc.segments, sc.bounds)
         w.set_state(sc.x, sc.y, sc.heading, sc.speed, vx=sc.vx, vy=sc.vy, type_id=sc.type_id)
@@ -454,7 +460,7 @@ def run_ours(args):
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.sharded else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": scene0.name, "scenarios_per_gpu": n, "participants": m, "model": "SingleTrackKinematics" if args.config in ("c2", "c5") else args.config,
                        "interval_ms": 100, "delta_t_ms": 5, "map_segments": 0 if scene0.segments is None else int(len(scene0.segments)),
@@ -517,6 +523,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--replicas", type=int, default=0)
+    ap.add_argument("--scenarios", type=int, default=0, help="scenarios per GPU (with --sharded: of the whole job) instead of the configuration's")
+    ap.add_argument("--sharded", action="store_true", help="strong scaling: the configuration's scenarios are split across the ranks")
     ap.add_argument("--min-reps", type=int, default=5)
     ap.add_argument("--max-reps", type=int, default=400)
     ap.add_argument("--min-seconds", type=float, default=2.0)
