@@ -30,11 +30,30 @@ def _world(scene, device, **kw):
     return w
 
 
+class _CompiledOracle:
+    """The float64 oracle in C + OpenMP (oracle/c/oracle_tick.c; held to the NumPy oracle at 1e-12 by
+    tests/test_oracle_c.py): the same two entry points as oracle.scenario, fast enough for full BASELINE sizes."""
+
+    @staticmethod
+    def physics_tick(state, type_id, action, table, interval=100, delta_t=5, steer_first=False):
+        from oracle import c_oracle as CO
+
+        return CO.physics(state, type_id, action, table, interval, delta_t, steer_first)
+
+    @staticmethod
+    def events(x, y, heading, type_id, table, segments=None, bounds=None):
+        from oracle import c_oracle as CO
+
+        return CO.events(x, y, heading, type_id, table, segments, bounds)
+
+
 def _teacher_forced(scene, device, steps, seed=0, interval=100, delta_t=5, max_step=0, any_participant=False,
-                    steer_first=False, action_fn=None, rtol=1e-5):
+                    steer_first=False, action_fn=None, rtol=1e-5, compiled=False):
     import torch
 
     from tactics2d_b200 import synthetic
+
+    P = _CompiledOracle if compiled else O   # who restates the physics and the events
 
     n, m = scene.shape
     w = _world(scene, device, interval=interval, delta_t=delta_t, max_step=max_step, any_participant=any_participant,
@@ -45,7 +64,7 @@ def _teacher_forced(scene, device, steps, seed=0, interval=100, delta_t=5, max_s
     for t in range(steps):
         before = w.state_numpy()
         act = action_fn(t) if action_fn else synthetic.random_actions(seed * 1000 + t, (n, m))
-        ref = O.physics_tick(before, scene.type_id, act, table, interval, delta_t, steer_first)
+        ref = P.physics_tick(before, scene.type_id, act, table, interval, delta_t, steer_first)
         r = w.step(torch.from_numpy(act).to(device))
         torch.cuda.synchronize()
         got = w.state_numpy()
@@ -56,7 +75,7 @@ def _teacher_forced(scene, device, steps, seed=0, interval=100, delta_t=5, max_s
         # inactive slots pass through untouched
         for k in ("x", "y", "heading", "speed", "vx", "vy"):
             assert np.array_equal(got[k][~active], before[k][~active])
-        fl, hi, hs = O.events(got["x"], got["y"], got["heading"], scene.type_id, table, scene.segments, scene.bounds)
+        fl, hi, hs = P.events(got["x"], got["y"], got["heading"], scene.type_id, table, scene.segments, scene.bounds)
         gfl, ghi, ghs = r.flags.cpu().numpy(), r.hit_index.cpu().numpy(), r.hit_segment.cpu().numpy()
         assert np.array_equal(gfl, fl), f"flags differ at step {t}: {np.argwhere(gfl != fl)[:5]}"
         assert np.array_equal(ghi, hi), f"hit_index differs at step {t}: {np.argwhere(ghi != hi)[:5]}"
@@ -386,3 +405,96 @@ def test_step_host_equals_step(cuda_device, monkeypatch, n, m, chunks):
         assert np.array_equal(ra.done.cpu().numpy(), done)
         seen_done += int(done.sum())
     assert seen_done > 0
+
+
+# ---------------------------------------------------------------------------- every BASELINE configuration at full size
+# (checker: the compiled float64 oracle; >= 3 teacher-forced steps each; every state within 1e-5, every flag / index /
+#  status / done bit-exact)
+def test_full_size_config2_three_steps_compiled_oracle(cuda_device):
+    from tactics2d_b200 import synthetic
+
+    scene = synthetic.config2(4096, 64, seed=1)
+    stats = _teacher_forced(scene, cuda_device, 3, seed=19, compiled=True)
+    assert stats["dyn"] > 3000 and stats["static"] > 15000
+
+
+def test_full_size_config3_dynamics_on_highD(cuda_device):
+    """configs[2]: 4096 x 64 SingleTrackDynamics on the highD_1 tile."""
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("highD_1")
+    scene = synthetic.config3(4096, 64, seed=23, segments=seg, bounds=bounds)
+    act = lambda t: synthetic.random_actions(2300 + t, scene.shape, accel=(-6, 3), steer=(-0.05, 0.05))
+    stats = _teacher_forced(scene, cuda_device, 3, action_fn=act, any_participant=True, compiled=True)
+    assert stats["static"] > 0 and stats["dyn"] > 0
+
+
+def test_full_size_config4_mixed_on_inD(cuda_device):
+    """configs[3]: 16384 x 32 vehicles / cyclists / pedestrians on the inD_1 intersection."""
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("inD_1")
+    scene = synthetic.config4(16384, 32, seed=24, segments=seg, bounds=bounds)
+    act = lambda t: synthetic.random_actions(2400 + t, scene.shape, accel=(-3, 3), steer=(-0.8, 0.8))
+    stats = _teacher_forced(scene, cuda_device, 3, action_fn=act, any_participant=True, compiled=True)
+    assert stats["static"] > 1000 and stats["dyn"] > 1000
+
+
+def test_large_config5_m128_on_rounD(cuda_device):
+    """configs[4] at one GPU's share of the 8-GPU job: 8192 x 128 kinematic vehicles on rounD_0 (more warp tiles than
+    the GPU holds at once: the persistent CTAs loop)."""
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("rounD_0")
+    scene = synthetic.config5(8192, 128, seed=25, segments=seg, bounds=bounds)
+    stats = _teacher_forced(scene, cuda_device, 3, seed=25, any_participant=True, compiled=True)
+    assert stats["static"] > 1000 and stats["dyn"] > 1000
+
+
+def _free_rollout(scene, device, steps, action_fn, budget, **kw):
+    """GPU and float64 oracle both run FREE from the same initial state (the oracle never sees the GPU's states): the
+    trajectories may drift apart by rounding only - position / speed error within `budget` (relative to max(|ref|, 1))
+    after `steps` ticks; participants that touch anything are excluded from then on (a flag flips one ulp apart)."""
+    import torch
+
+    n, m = scene.shape
+    w = _world(scene, device, **kw)
+    table = scene.table.as_oracle_table()
+    ref = {k: v.astype(np.float64) for k, v in scene.state().items()}
+    worst = 0.0
+    for t in range(steps):
+        act = action_fn(t)
+        ref = _CompiledOracle.physics_tick({k: v.astype(np.float32) for k, v in ref.items()}, scene.type_id, act, table)
+        w.step(torch.from_numpy(act).to(device))
+    torch.cuda.synchronize()
+    got = w.state_numpy()
+    active = scene.type_id != 255
+    for k in ("x", "y", "speed"):
+        worst = max(worst, float(np.max(rel_err(got[k], ref[k])[active])))
+    worst = max(worst, float(np.max(heading_err(got["heading"], ref["heading"])[active])))
+    w.close()
+    assert worst <= budget, worst
+    return worst
+
+
+def test_free_rollout_50_steps_config2(cuda_device):
+    """50 free-running ticks at C2 (1024 x 64): fp32 state against the float64 oracle fed its own fp32-rounded states.
+    Budget 5e-4: ~1e-5 per tick at most, errors do not compound beyond linear growth over 50 ticks."""
+    from tactics2d_b200 import synthetic
+
+    scene = synthetic.config2(1024, 64, seed=31)
+    act = lambda t: synthetic.random_actions(3100 + t, scene.shape)
+    _free_rollout(scene, cuda_device, 50, act, 5e-4)
+
+
+def test_free_rollout_50_steps_config4(cuda_device):
+    from tactics2d_b200 import synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("inD_1")
+    scene = synthetic.config4(1024, 32, seed=34, segments=seg, bounds=bounds)
+    act = lambda t: synthetic.random_actions(3400 + t, scene.shape, accel=(-3, 3), steer=(-0.8, 0.8))
+    _free_rollout(scene, cuda_device, 50, act, 5e-4)

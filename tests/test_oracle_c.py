@@ -39,3 +39,31 @@ def test_c_oracle_steer_first():
     b = O.physics_tick(scene.state(), scene.type_id, act, table, steer_first=True)
     for k in b:
         np.testing.assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-12)
+
+
+def test_dynamics_low_speed_band_is_ill_conditioned_between_two_float64_implementations():
+    """Why |v| in (0.1, 0.45) m/s is outside the SingleTrackDynamics parity domain (DESIGN.md "numerics"): the reference's
+    explicit Euler of the yaw-rate / slip equations multiplies a perturbation by |1 - 1.34 / v| per 5 ms sub-step.  Two
+    float64 evaluations of the SAME operation order - this NumPy restatement and the C restatement built with
+    -ffp-contract=off, which differ only in the last bit of libm's tan / atan / sincos - already disagree by far more than
+    the 1e-5 tolerance below ~0.35 m/s, while they agree to 1e-7 from 0.45 m/s up.  No device implementation can be held
+    to the reference there; nothing about fp32 or FMA contraction is involved."""
+    from oracle import scenario as O
+    from tactics2d_b200.types import TypeTable
+
+    t = TypeTable.from_templates("dynamics").as_oracle_table()
+    rng = np.random.default_rng(0)
+    n = 4000
+    worst = {}
+    for lo, hi in ((0.1, 0.25), (0.25, 0.35), (0.45, 1.0)):
+        v = rng.uniform(lo, hi, (n, 1)).astype(np.float32)
+        st = dict(x=np.zeros((n, 1), np.float32), y=np.zeros((n, 1), np.float32), heading=rng.uniform(0, 6, (n, 1)).astype(np.float32),
+                  speed=v, vx=v * 0, vy=v * 0)
+        tid = np.full((n, 1), 4, np.uint8)
+        act = np.stack([np.zeros((n, 1)), rng.uniform(-0.5, 0.5, (n, 1))], -1).astype(np.float32)
+        a = O.physics_tick(st, tid, act, t, 100, 5)
+        c = CO.physics(st, tid, act, t, 100, 5)
+        d = np.abs(a["heading"] - c["heading"])
+        worst[(lo, hi)] = float(np.minimum(d, 2 * np.pi - d).max())
+    assert worst[(0.1, 0.25)] > 1e-2 and worst[(0.25, 0.35)] > 1e-5, worst   # float64 vs float64: no agreement
+    assert worst[(0.45, 1.0)] < 1e-6, worst                                   # the parity domain: agreement
