@@ -127,28 +127,32 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def _cpu_worker(args):
+_CPU_JOB = {}   # filled before the worker pool forks: the workers share the batch copy-on-write and receive only index ranges
+
+
+def _cpu_worker(rng):
     from oracle import scalar_port as SP
 
-    state, tid, act, table, seg, bounds = args
-    t = time.perf_counter()
-    SP.tick_scenarios(state, tid, act, table, seg, bounds)
-    return time.perf_counter() - t
+    lo, hi = rng
+    j = _CPU_JOB
+    SP.tick_scenarios({k: v[lo:hi] for k, v in j["state"].items()}, j["tid"][lo:hi], j["act"][lo:hi], j["table"], j["seg"], j["bounds"])
+    return hi - lo
 
 
-def cpu_port_throughput(scene, n_scn: int, procs: int, steps: int = 1, warmup: int = 0):
-    """participant-steps/s of the reference-style per-agent Python loop on `n_scn` scenarios per step."""
+def cpu_port_throughput(scene, n_scn: int, procs: int, steps: int = 1, warmup: int = 0, per_job: int = 32):
+    """participant-steps/s of the reference-style per-agent Python loop over the first `n_scn` scenarios per step, fanned
+    over `procs` worker processes in jobs of `per_job` scenarios (a job of one scenario would time the pool's dispatch,
+    not the loop)."""
     import multiprocessing as mp
 
     from tactics2d_b200 import synthetic
 
-    table = scene.table.as_oracle_table()
     n_scn = min(n_scn, scene.shape[0])
-    st = {k: v[:n_scn] for k, v in scene.state().items()}
-    tid = scene.type_id[:n_scn]
-    act = synthetic.random_actions(77, (n_scn, scene.shape[1]))
-    chunks = np.array_split(np.arange(n_scn), max(1, min(procs, n_scn)))
-    jobs = [({k: v[c] for k, v in st.items()}, tid[c], act[c], table, scene.segments, scene.bounds) for c in chunks if len(c)]
+    _CPU_JOB.update(state={k: v[:n_scn] for k, v in scene.state().items()}, tid=scene.type_id[:n_scn],
+                    act=synthetic.random_actions(77, (n_scn, scene.shape[1])), table=scene.table.as_oracle_table(),
+                    seg=scene.segments, bounds=scene.bounds)
+    per_job = max(1, min(per_job, -(-n_scn // max(1, procs))))
+    jobs = [(lo, min(lo + per_job, n_scn)) for lo in range(0, n_scn, per_job)]
     times = []
     if procs <= 1:
         for i in range(warmup + steps):
@@ -161,7 +165,7 @@ def cpu_port_throughput(scene, n_scn: int, procs: int, steps: int = 1, warmup: i
         with mp.get_context("fork").Pool(procs) as pool:
             for i in range(warmup + steps):
                 t = time.perf_counter()
-                pool.map(_cpu_worker, jobs)
+                pool.map(_cpu_worker, jobs, chunksize=1)
                 if i >= warmup:
                     times.append(time.perf_counter() - t)
     total = n_scn * scene.shape[1] * len(times)
@@ -186,20 +190,32 @@ def cpu_c_throughput(scene, reps=3):
 
 
 def run_reference(args):
+    """The reference's execution model for this path on the host cores, on the SAME configuration as the GPU arm: every
+    step is the whole batch (4096 x 64 at C2), 32 scenarios per job, one worker process per core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    scene = make_scene(args.config, seed=1, n=max(64, 2 * cores))
-    per_step = max(cores, 8)
-    value, t_step = cpu_port_throughput(scene, per_step, cores, steps=args.steps, warmup=args.warmup)
-    sample = (f"{per_step} of {N_SCN} scenarios x {scene.shape[1]} participants per step, {args.steps} steps, "
-              f"{cores} processes (per-agent Python loop, restatement: shapely/GEOS unavailable)")
+    scene = make_scene(args.config, seed=1, n=args.scenarios or None)
+    n, m = scene.shape
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # bounded: the whole run must end within a few minutes - ~2 k participant-steps/s per core measured for the port
+    est = n * m / (1900.0 * max(1, cores)) * (steps + warmup)
+    if est > 240.0:
+        warmup = min(warmup, 1)
+        steps = max(1, min(steps, int(240.0 / max(1e-9, n * m / (1900.0 * cores))) - warmup))
+    value, t_step = cpu_port_throughput(scene, n, cores, steps=steps, warmup=warmup, per_job=32)
+    sample = (f"the whole batch every step: {n} scenarios x {m} participants, {steps} timed steps after {warmup} warm-up, "
+              f"{cores} worker processes x jobs of 32 scenarios (per-agent Python loop = the reference's execution model; "
+              f"a restatement: shapely/GEOS and gymnasium are not installable here, oracle/scalar_port.py)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": make_scene_name(args.config), "sample_scenarios_per_step": per_step, "seed": 1},
+        "config": {"workload": scene.name, "scenarios_per_gpu": n, "participants": m,
+                   "model": "SingleTrackKinematics" if args.config in ("c2", "c5") else args.config,
+                   "interval_ms": 100, "delta_t_ms": 5, "map_segments": 0 if scene.segments is None else int(len(scene.segments)),
+                   "timed_steps": steps},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
