@@ -255,8 +255,9 @@ int t2d_control(t2d_ctx* ctx, float* action, void* stream);
  * t2d_set_ego_action binds a DEVICE array [N][2] (or NULL to unbind): while bound, t2d_control and t2d_step take the
  * action of participant 0 of every scenario from it (t2d_control also writes it into row 0 of `action`). */
 int t2d_set_ego_action(t2d_ctx* ctx, const float* ego_action /* device [N][2], 8-byte aligned */);
-/* One tick for a caller whose policy lives on the host and drives only the ego: copies ego_action_host [N][2] to the
- * device (8 N bytes instead of the 8 N M of t2d_step_host), runs t2d_control when controllers are set (the other
+/* One tick for a caller whose policy lives on the host and drives only the ego: stages ego_action_host [N][2] in pinned,
+ * device-mapped host memory that the first kernel reads directly (8 N bytes over PCIe instead of the 8 N M of
+ * t2d_step_host, and no copy-engine transfer in front of the kernels), runs t2d_control when controllers are set (the other
  * participants' rows of `action`, a DEVICE array [N][M][2] owned by the caller, never leave the device), the tick, and
  * copies status + done back ([N] each, HOST); synchronises `stream` before returning. */
 int t2d_step_host_ego(t2d_ctx* ctx, const float* ego_action_host, float* action, uint8_t* flags, int16_t* hit_index,

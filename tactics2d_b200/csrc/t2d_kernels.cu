@@ -1462,7 +1462,7 @@ __device__ double longitudinal_law(const t2d_controller_params& p, double v, dou
   const double kp = (double)p.kp;
   double a;
   if (has_lead) {
-    const double d_front = hypot(x - xl, y - yl);                                            // :114
+    const double d_front = sqrt((x - xl) * (x - xl) + (y - yl) * (y - yl));                  // :114
     const double d_target = clip_np(v * (double)p.interval + 5.0, 7.0, 80.0);                // :115-118, :42-45
     const double rel_speed = vl - v;                                                         // :120
     const double rel_target_speed = (d_target - d_front) / kp;                               // :121
@@ -1476,20 +1476,27 @@ __device__ double longitudinal_law(const t2d_controller_params& p, double v, dou
   return clip_np(a, (double)p.min_accel, (double)p.max_accel);
 }
 
+// (v / v_des) ** delta: the IDM exponent is 4 by default - two multiplications instead of the general pow()
+__device__ __forceinline__ double idm_pow(double r, double delta) {
+  if (delta == 4.0) { const double r2 = r * r; return r2 * r2; }
+  if (delta == 2.0) return r * r;
+  return pow(r, delta);
+}
+
 // idm_controller.py:59-141
 __device__ double idm_law(const t2d_controller_params& p, double v, double x, double y, bool has_lead, double vl, double xl,
                           double yl) {
   const double vd = (double)p.desired_speed, am = (double)p.max_acceleration, b = (double)p.comfortable_deceleration;
   double a;
   if (!has_lead) {
-    a = vd > 0.0 ? am * (1.0 - pow(v / vd, (double)p.delta)) : (v > 0.0 ? -b : 0.0);         // :74-82
+    a = vd > 0.0 ? am * (1.0 - idm_pow(v / vd, (double)p.delta)) : (v > 0.0 ? -b : 0.0);     // :74-82
   } else {
-    const double dist = hypot(xl - x, yl - y);                                               // :107-109
+    const double dist = sqrt((xl - x) * (xl - x) + (yl - y) * (yl - y));                     // :107-109 (np.hypot, no overflow concern at map scale)
     const double dv = vl - v;                                                                // :112
     double s_star = (double)p.min_spacing + v * (double)p.time_headway + (v * dv) / (2.0 * sqrt(am * b));   // :116-120
     s_star = fmax(s_star, (double)p.min_spacing);                                            // :121
     if (dist > 0.0) {
-      const double ratio = vd > 0.0 ? pow(v / vd, (double)p.delta) : (v > 0.0 ? 1.0 : 0.0);  // :127-130
+      const double ratio = vd > 0.0 ? idm_pow(v / vd, (double)p.delta) : (v > 0.0 ? 1.0 : 0.0);  // :127-130
       const double q = s_star / dist;
       a = am * (1.0 - ratio - q * q);                                                        // :132-134
     } else {
@@ -1663,7 +1670,8 @@ struct t2d_ctx {
   // t2d_step_host: device staging for the host-resident action / status / done, the copy stream and its events
   static constexpr int MAX_HOST_CHUNKS = 8;
   float* hs_action = nullptr;          // [N][M][2]
-  float* hs_ego = nullptr;             // [N][2] (t2d_step_host_ego)
+  float* hs_ego_pinned = nullptr;      // [N][2] pinned + mapped host staging of the ego actions (t2d_step_host_ego) ...
+  const float* hs_ego_dev = nullptr;   // ... and its device-side address: the kernels read it over PCIe, no copy engine involved
   uint8_t* hs_out = nullptr;           // [2][N] status, done
   uint8_t* hs_out_pinned = nullptr;    // pinned host mirror of hs_out
   cudaStream_t hs_copy = nullptr;
@@ -1736,7 +1744,7 @@ int t2d_destroy(t2d_ctx* c) {
   if (c->d_path_v) cudaFree(c->d_path_v);
   if (c->d_path_off) cudaFree(c->d_path_off);
   if (c->hs_action) cudaFree(c->hs_action);
-  if (c->hs_ego) cudaFree(c->hs_ego);
+  if (c->hs_ego_pinned) cudaFreeHost(c->hs_ego_pinned);
   if (c->hs_out) cudaFree(c->hs_out);
   if (c->hs_out_pinned) cudaFreeHost(c->hs_out_pinned);
   if (c->hs_begin) cudaEventDestroy(c->hs_begin);
@@ -2214,17 +2222,31 @@ int t2d_step_host_ego(t2d_ctx* c, const float* ego_action_host, float* action, u
   if (!ego_action_host || !action) return fail(T2D_E_INVALID, "ego_action / action is NULL");
   CUDA_TRY(cudaSetDevice(c->device));
   const int N = c->N;
-  if (!c->hs_ego) CUDA_TRY(cudaMalloc(&c->hs_ego, (size_t)N * 2 * sizeof(float)));
+  if (!c->hs_ego_pinned) {
+    // pinned AND mapped: the first kernel of the step reads the 8 N bytes straight from host memory (one PCIe round trip
+    // inside the kernel) instead of waiting for a copy-engine transfer and the stream dependency behind it
+    CUDA_TRY(cudaHostAlloc(&c->hs_ego_pinned, (size_t)N * 2 * sizeof(float), cudaHostAllocMapped));
+    float* dev = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&dev, c->hs_ego_pinned, 0));
+    c->hs_ego_dev = dev;
+  }
   if (!c->hs_out) {
     CUDA_TRY(cudaMalloc(&c->hs_out, 2 * (size_t)N));
     CUDA_TRY(cudaMallocHost(&c->hs_out_pinned, 2 * (size_t)N));
   }
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(c->hs_ego, ego_action_host, (size_t)N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  memcpy(c->hs_ego_pinned, ego_action_host, (size_t)N * 2 * sizeof(float));
   const float* saved = c->ego_action;
-  c->ego_action = c->hs_ego;
   int r = T2D_OK;
-  if (c->d_ctab) r = t2d_control(c, action, stream);   // the other participants' actions never leave the device
+  if (c->d_ctab) {
+    // the controllers' launch fetches the ego actions and writes them into row 0 of `action`; the other participants'
+    // actions never leave the device; the tick then reads everything from `action`
+    c->ego_action = c->hs_ego_dev;
+    r = t2d_control(c, action, stream);
+    c->ego_action = nullptr;
+  } else {
+    c->ego_action = c->hs_ego_dev;
+  }
   if (r == T2D_OK) r = launch_step(c, action, flags, hit_index, hit_segment, c->hs_out, c->hs_out + N, stream, 1);
   c->ego_action = saved;
   if (r != T2D_OK) return r;
