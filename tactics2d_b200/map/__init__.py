@@ -30,7 +30,10 @@ import numpy as np
 
 TILE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tiles")
 
-# RoadLine kinds a vehicle cannot cross (roadline.py:107-123)
+# RoadLine kinds that are physical structures a vehicle cannot drive through.  The reference gives every one of them the
+# lane-change rule (False, False): type curbstone / road_border at roadline.py:109-110, subtypes guard_rail, wall, fence,
+# jersey_barrier, gate, door, rail at roadline.py:111-124.  The PAINTED members of that same list (zebra_marking,
+# pedestrian_marking, bike_marking, keepout, roadline.py:115-118) carry the same rule but are not obstacles and stay out.
 BARRIER_TYPES = ("curbstone", "road_border", "guard_rail", "wall", "fence", "jersey_barrier", "gate", "door", "rail")
 
 
