@@ -148,6 +148,31 @@ int t2d_set_type_table(t2d_ctx* ctx, const t2d_type_params* table, int n_types);
  * in metres (<= 0: choose automatically). */
 int t2d_set_map(t2d_ctx* ctx, const float* segments, int n_seg, const float* bounds, float cell_size);
 
+/* Static objects that are AREAS, and a different map per scenario.
+ * StaticCollision.update tests `agent_pose.intersects(static_object.geometry)` against a list of static objects
+ * (traffic/event_detection/collision.py:37-43); in the reference's envs those are Area polygons - the walls and obstacles
+ * of a parking lot, regenerated by every reset (envs/parking.py:397-441) - and a pose wholly inside a polygon intersects
+ * it without touching an edge.  poly_start (host int32 [n_poly + 1], ascending) marks the segments that close up to
+ * rings: ring p = segments [poly_start[p], poly_start[p + 1]), each edge ending where the next begins and the last at the
+ * first one's start (Area.geometry's exterior); segments outside every ring are open polyline pieces (RoadLine).
+ * With rings present, hit_segment names the first OBJECT hit in list order by its first segment: poly_start[p] for ring p
+ * (an edge of it was touched, or the pose centre lies inside it), the segment itself for an open piece. */
+int t2d_set_map_polygons(t2d_ctx* ctx, const float* segments, int n_seg, const int32_t* poly_start, int n_poly,
+                         const float* bounds, float cell_size);
+/* One tile = the static objects + boundary of one map (host arrays, copied).  tile_id: DEVICE uint16 [N], owned by the
+ * caller and read by every tick: the tile of each scenario (may be rewritten between ticks, e.g. by a reset that draws a
+ * new parking lot); NULL is allowed when n_tiles == 1.  Every scenario then collides with its own tile's objects, is
+ * bounded by its own tile's box, and t2d_lidar_scan sees its own tile's segments. */
+#define T2D_MAX_TILES 4096
+typedef struct {
+  const float* segments;     /* [n_seg][4] */
+  int32_t n_seg;
+  const int32_t* poly_start; /* [n_poly + 1] or NULL */
+  int32_t n_poly;
+  const float* bounds;       /* [4] xmin, xmax, ymin, ymax or NULL */
+} t2d_map_tile;
+int t2d_set_map_table(t2d_ctx* ctx, const t2d_map_tile* tiles, int n_tiles, const uint16_t* tile_id, float cell_size);
+
 /* DEVICE pointers, each [N, M] (step_count: [N]); read and written in place by t2d_step. */
 int t2d_bind_state(t2d_ctx* ctx, float* x, float* y, float* heading, float* speed, float* vx, float* vy,
                    const uint8_t* type_id, int32_t* step_count);

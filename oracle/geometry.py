@@ -134,3 +134,19 @@ def rect_iou(xa, ya, ha, la, wa, xb, yb, hb, lb, wb):
                           for i in range(len(poly)))) if poly else 0.0
     union = 4.0 * la * wa + 4.0 * lb * wb - inter
     return inter / union if union > 0 else 0.0
+
+
+def point_in_ring(px, py, ring):
+    """Even-odd (crossing number) point-in-polygon for points ``px, py`` (arrays) against the closed ring given by its
+    edges ``ring`` [E, 4] = (x1, y1, x2, y2): what ``Polygon.contains`` / ``intersects`` decides for a point strictly
+    inside or outside (shapely's Area.geometry, area.py:13-125).  Points on the boundary are not this function's business:
+    a pose whose centre is that close to an edge intersects the edge itself."""
+    px, py = np.asarray(px, dtype=np.float64), np.asarray(py, dtype=np.float64)
+    ring = np.asarray(ring, dtype=np.float64)
+    inside = np.zeros(px.shape, bool)
+    for x1, y1, x2, y2 in ring:
+        straddle = (y1 > py) != (y2 > py)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xint = (x2 - x1) * (py - y1) / (y2 - y1) + x1
+        inside ^= straddle & (px < xint)
+    return inside

@@ -106,13 +106,18 @@ def physics_tick(state, type_id, action, table, interval=100, delta_t=5, steer_f
     return out
 
 
-def events(x, y, heading, type_id, table, segments=None, bounds=None, chunk=64):
+def events(x, y, heading, type_id, table, segments=None, bounds=None, chunk=64, poly_start=None):
     """Collision / out-of-bound events on the given poses.
 
     Returns ``flags`` uint8 [N, M] (bit0 dynamic, bit1 static, bit2 out-of-bound),
     ``hit_index`` int16 [N, M] (lowest colliding participant index or -1:
     collision.py:18-25 iterates in list order and breaks on the first hit) and
     ``hit_segment`` int16 [N, M] (lowest colliding map segment or -1, collision.py:37-43).
+
+    ``poly_start`` [P + 1]: the segments [poly_start[p], poly_start[p + 1]) are the edges of a closed Area polygon.  The
+    reference tests ``agent_pose.intersects(static_object.geometry)`` object by object (collision.py:37-43): a polygon is
+    hit when one of its edges meets the pose OR the pose lies inside it (a pose inside and clear of every edge contains its
+    own centre, so "centre in polygon" decides); ``hit_segment`` then names the first OBJECT hit by its first segment.
     """
     x, y, heading = (np.asarray(a, dtype=np.float64) for a in (x, y, heading))
     N, M = x.shape
@@ -147,7 +152,18 @@ def events(x, y, heading, type_id, table, segments=None, bounds=None, chunk=64):
             cs = G.circle_segment(A(x), A(y), A(r), S(0), S(1), S(2), S(3))
             sh = np.where(ca, cs, os_) & A(solid)
             any_s = sh.any(-1)
-            hit_segment[sl] = np.where(any_s, sh.argmax(-1), -1).astype(np.int16)
+            first = np.where(any_s, sh.argmax(-1), np.iinfo(np.int32).max).astype(np.int64)
+            if poly_start is not None and len(poly_start) > 1:
+                ps = np.asarray(poly_start, dtype=np.int64)
+                obj_first = np.arange(len(seg), dtype=np.int64)
+                for p0, p1 in zip(ps[:-1], ps[1:]):
+                    obj_first[p0:p1] = p0
+                first = np.where(any_s, obj_first[np.minimum(first, len(seg) - 1)], first)
+                for p0, p1 in zip(ps[:-1], ps[1:]):
+                    inside = G.point_in_ring(x[sl], y[sl], seg[p0:p1]) & solid[sl]
+                    first = np.where(inside & (p0 < first), p0, first)
+                any_s = first < np.iinfo(np.int32).max
+            hit_segment[sl] = np.where(any_s, first, -1).astype(np.int16)
             flags[sl] |= np.where(any_s, F_STATIC, 0).astype(np.uint8)
 
     if bounds is not None:

@@ -30,6 +30,12 @@ class TypeParamsC(C.Structure):
         ("model", C.c_int32), ("shape", C.c_int32)] + [(n, C.c_float) for n in ("wheel_radius", "T_sb", "T_se", "I_yw")]
 
 
+class MapTileC(C.Structure):
+    """``t2d_map_tile``: the static objects and the boundary of one map (host pointers)."""
+    _fields_ = [("segments", C.c_void_p), ("n_seg", C.c_int32), ("poly_start", C.c_void_p), ("n_poly", C.c_int32),
+                ("bounds", C.c_void_p)]
+
+
 class ControllerParamsC(C.Structure):
     """``t2d_controller_params``: one configured controller object."""
     _fields_ = [("kind", C.c_int32)] + [(n, C.c_float) for n in (
@@ -48,6 +54,8 @@ SYMBOLS = {
     "t2d_set_config": (C.c_int, [_P, C.POINTER(Config)]),
     "t2d_set_type_table": (C.c_int, [_P, C.POINTER(TypeParamsC), C.c_int]),
     "t2d_set_map": (C.c_int, [_P, _P, C.c_int, _P, C.c_float]),
+    "t2d_set_map_polygons": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_float]),
+    "t2d_set_map_table": (C.c_int, [_P, _P, C.c_int, _P, C.c_float]),
     "t2d_bind_state": (C.c_int, [_P] + [_P] * 8),
     "t2d_step": (C.c_int, [_P] + [_P] * 7),
     "t2d_step_host": (C.c_int, [_P] + [_P] * 7),

@@ -43,7 +43,7 @@ constexpr int CTA_THREADS = MAX_WARPS_PER_CTA * 32;   // upper bound; the host p
 constexpr int POSE_PER_WARP = 128;      // 32 lanes x 4 participants per lane (PPL, template parameter of K1: 2 or 4)
 constexpr int MAP_SMEM_LIMIT = 120 * 1024;
 
-struct MapHeader {   // 96 bytes, start of the map blob
+struct MapHeader {   // 128 bytes, start of a tile's blob
   int32_t n_seg, gx, gy, n_items;
   float x0, y0, inv_cell, cell;
   uint32_t off_seg, off_cell, off_items, total_bytes;
@@ -55,10 +55,18 @@ struct MapHeader {   // 96 bytes, start of the map blob
   uint32_t off_dcell, off_ditems;
   float dil;
   int32_t n_ditems;
-  uint32_t pad[6];
+  uint32_t off_objfirst;   // uint16 per segment: first segment of the object (polygon / polyline piece) it belongs to
+  int32_t n_poly;          // closed rings among the segments (Area.geometry polygons)
+  uint32_t off_poly;       // int32 [n_poly + 1]: ring p = segments [start[p], start[p + 1])
+  uint32_t off_pbox;       // float4 per ring: xmin, xmax, ymin, ymax
+  uint32_t off_fine;       // the fine clearance field (bytes), last section of the blob
+  uint32_t smem_bytes;     // = off_fine: the part worth staging into shared memory
+  float bxmin, bxmax, bymin, bymax;   // Map.boundary of the tile (OutBound)
+  int32_t has_bounds;
+  uint32_t pad[3];
 };
 constexpr float CLEAR_QUANT = 0.125f;   // metres per unit of the byte-quantised fine clearance field
-static_assert(sizeof(MapHeader) == 96, "MapHeader must be 96 bytes");
+static_assert(sizeof(MapHeader) == 128, "MapHeader must be 128 bytes");
 
 struct StepArgs {
   float *x, *y, *h, *v, *vx, *vy;
@@ -71,8 +79,9 @@ struct StepArgs {
   int16_t* hit_segment;
   uint8_t* scn_status;
   uint8_t* done;
-  const unsigned char* map_blob;   // device; nullptr when no segments
-  const uint8_t* map_fine;         // device; fine clearance field (bytes), read through L1/L2
+  const unsigned char* map_blob;   // device: the tiles' blobs, one after the other; nullptr when no tile has segments
+  const uint32_t* tile_off;        // [n_tiles] byte offset of every tile's blob (map table mode)
+  const uint16_t* tile_id;         // [N] the tile of every scenario, or nullptr: every scenario uses tile 0
   MapHeader mh;                    // copy of the blob header (grid geometry, section offsets): constant bank
   const Params* table;             // device
   int map_bytes, map_in_smem;
@@ -431,6 +440,32 @@ __device__ __forceinline__ int static_walk(int ti, const Pose& a, float rbound, 
   return overflow ? -2 : best;
 }
 
+// Area polygons (StaticCollision.update tests pose.intersects(area.geometry), collision.py:37-43): a pose that touches no
+// edge still intersects the closed polygon when it lies inside it.  `best` = the lowest edge hit so far (0x7fffffff: none);
+// returns the first segment of the first OBJECT hit: an edge hit is renamed to its object's first segment, and every ring
+// that starts below that and contains the pose centre takes over.  The crossing-number test runs in fp32: it is only
+// decisive for rings none of whose edges touch the pose, i.e. whose edges all stay at least the pose's inradius away from
+// the centre - far beyond fp32 rounding.
+__device__ __noinline__ int static_objects(int best, float px, float py, const MapHeader& mh, const unsigned char* blob) {
+  if (best != 0x7fffffff && best >= 0) best = reinterpret_cast<const uint16_t*>(blob + mh.off_objfirst)[best];
+  const int32_t* pstart = reinterpret_cast<const int32_t*>(blob + mh.off_poly);
+  const float4* pbox = reinterpret_cast<const float4*>(blob + mh.off_pbox);
+  const float4* seg = reinterpret_cast<const float4*>(blob + mh.off_seg);
+  for (int p = 0; p < mh.n_poly; ++p) {
+    const int s0 = pstart[p];
+    if (s0 >= best) break;
+    const float4 bb = pbox[p];
+    if (!(px >= bb.x && px <= bb.y && py >= bb.z && py <= bb.w)) continue;
+    bool in = false;
+    for (int i = s0; i < pstart[p + 1]; ++i) {
+      const float4 e = seg[i];
+      if ((e.y > py) != (e.w > py) && px < (e.z - e.x) * (py - e.y) / (e.w - e.y) + e.x) in = !in;
+    }
+    if (in) { best = s0; break; }
+  }
+  return best;
+}
+
 // Out-of-line exact walk for a participant whose undecided segments did not fit the exact queue (never on the
 // hot path): the same cells, every test through the fp32 filter + fp64 fallback.
 __device__ __noinline__ int static_walk_exact(const Pose a, float rbound, const MapHeader mh, const float4* seg, const uint32_t* cell_start,
@@ -455,10 +490,18 @@ __device__ __noinline__ int static_walk_exact(const Pose a, float rbound, const 
 // can reach a wall at all; (2) those participants are compacted into a list with warp ballots; (3) the list is
 // processed one participant per lane (static_walk), so the divergent cell walks of ~15 % of the participants run
 // side by side instead of one after the other; (4) the few filter-undecided segments are settled in fp64.
-template <int PPL>
-__device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lane, const MapHeader& mh, const MapView& mv,
-                                             const float4* poseA, const float4* poseB, int* segmin, unsigned* queue, int* qcount) {
-  const float4* seg = mv.seg;
+// Where a participant's tile lives: one tile for everybody (header in the kernel's constant bank, sections in shared or
+// global memory), or a table of tiles indexed by the participant's scenario (headers and sections in global memory).
+struct TileRef {
+  const MapHeader* mh;         // header (constant bank, or global)
+  const unsigned char* sec;    // where the sections up to the fine field are read from (shared or global)
+  const unsigned char* blob;   // the blob in global memory (fine field, polygon data)
+};
+
+template <int PPL, bool MAP_TABLE>
+__device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lane, int tile_first_scn, int mp_shift, const StepArgs& A,
+                                             const unsigned char* s_map, const float4* poseA, const float4* poseB, int* segmin,
+                                             unsigned* queue, int* qcount) {
   int base = 0;
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
@@ -468,11 +511,24 @@ __device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lan
     base += __popc(m);
   }
   constexpr int psh = PPL == 4 ? 2 : 1;
+  // the tile of participant slot ti (its scenario = the warp tile's first scenario + ti / padded participants)
+  auto tile_of = [&](int ti) {
+    TileRef t;
+    if constexpr (MAP_TABLE) {
+      const long long n = (long long)tile_first_scn + (ti >> mp_shift);
+      const unsigned char* blob = A.map_blob + A.tile_off[n < A.N ? A.tile_id[n] : 0];
+      t.mh = reinterpret_cast<const MapHeader*>(blob); t.sec = blob; t.blob = blob;
+    } else {
+      t.mh = &A.mh; t.sec = A.map_in_smem ? s_map : A.map_blob; t.blob = A.map_blob;
+    }
+    return t;
+  };
   __syncwarp();
   for (int k = lane; k < base; k += 32) {
     const int ti = (int)queue[k];
+    const TileRef t = tile_of(ti);
     const Pose a = load_pose(poseA, poseB, ti, psh);
-    const int best = static_walk(ti, a, poseA[pslot(ti, psh)].z, mh, mv, queue, qcount);
+    const int best = t.mh->n_seg > 0 ? static_walk(ti, a, poseA[pslot(ti, psh)].z, *t.mh, map_view(t.sec, *t.mh), queue, qcount) : 0x7fffffff;
     segmin[pslot(ti, psh)] = best;   // one lane per participant: plain store (-2 = needs the exact walk)
   }
   __syncwarp();
@@ -481,12 +537,24 @@ __device__ __forceinline__ void static_phase(unsigned near_bits, int t0, int lan
     const unsigned e = queue[QX0 + k];
     const int ti = (int)(e >> 16), sidx = (int)(e & 0xffffu);
     int* sm = &segmin[pslot(ti, psh)];
-    if (*sm != -2 && sidx < *sm && seg_exact(load_pose(poseA, poseB, ti, psh), seg[sidx])) atomicMin(sm, sidx);
+    if (*sm != -2 && sidx < *sm) {
+      const TileRef t = tile_of(ti);
+      if (seg_exact(load_pose(poseA, poseB, ti, psh), reinterpret_cast<const float4*>(t.sec + t.mh->off_seg)[sidx])) atomicMin(sm, sidx);
+    }
   }
-  for (int k = lane; k < base; k += 32) {   // exact-queue overflow (pathological): redo those participants out of line
+  __syncwarp();
+  for (int k = lane; k < base; k += 32) {   // the out-of-line walk where needed; then edges -> objects, polygon containment
     const int ti = (int)queue[k];
     int* sm = &segmin[pslot(ti, psh)];
-    if (*sm == -2) *sm = static_walk_exact(load_pose(poseA, poseB, ti, psh), poseA[pslot(ti, psh)].z, mh, mv.seg, mv.cell_start, mv.items);
+    const TileRef t = tile_of(ti);
+    if (*sm == -2) {
+      const MapView mv = map_view(t.sec, *t.mh);
+      *sm = static_walk_exact(load_pose(poseA, poseB, ti, psh), poseA[pslot(ti, psh)].z, *t.mh, mv.seg, mv.cell_start, mv.items);
+    }
+    if (t.mh->n_poly > 0) {
+      const float4 pa = poseA[pslot(ti, psh)];
+      *sm = static_objects(*sm, pa.x, pa.y, *t.mh, t.blob);
+    }
   }
   __syncwarp();
 }
@@ -529,13 +597,16 @@ __device__ __noinline__ unsigned ego_goal_events(const StepArgs& A, long long n,
 #else
 #define T2D_K1_BOUNDS __launch_bounds__(CTA_THREADS, (PPL == 4 ? 2 : 3))
 #endif
-template <int PPL, bool KIN_ONLY>
+// MAP_TABLE: every scenario names its own static-geometry tile (t2d_set_map_table); the tiles are then read from global
+// memory, header included.  Otherwise one tile serves all scenarios: header in the constant bank, sections staged into
+// shared memory once per CTA.
+template <int PPL, bool KIN_ONLY, bool MAP_TABLE>
 __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   // carve: [map blob | 16B aligned] [type table] [pose tiles, hit mins, queues, positions] [mbarrier]; every
   // offset, shift and count that depends only on the launch shape comes precomputed from the host
   // (kernel-parameter constant bank) instead of integer divisions / loops per thread
-  const int map_smem_bytes = A.map_in_smem ? A.map_bytes : 0;
+  const int map_smem_bytes = (!MAP_TABLE && A.map_in_smem) ? A.map_bytes : 0;
   const int table_bytes = A.table_bytes;
   const int wpc = A.wpc;
   unsigned char* s_map = smem;
@@ -809,11 +880,18 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     unsigned near_q[PPL], near_alt[PPL];
 #pragma unroll
     for (int i = 0; i < PPL; ++i) { near_q[i] = 255u; near_alt[i] = 255u; }   // 255 = far from every segment
-    if (A.map_blob != nullptr) {
+    // this lane's tile (all PPL participants of a lane belong to one scenario)
+    const MapHeader* lane_mh = &A.mh;
+    const unsigned char* lane_blob = A.map_blob;
+    if constexpr (MAP_TABLE) {
+      lane_blob = A.map_blob + A.tile_off[scn_ok ? A.tile_id[n] : 0];
+      lane_mh = reinterpret_cast<const MapHeader*>(lane_blob);
+    }
+    if (A.map_blob != nullptr && lane_mh->n_seg > 0) {
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
         unsigned alt;
-        near_q[i] = near_fetch(px[i], py[i], rb[i], A.mh, A.map_fine, alt);   // (a NaN position reads cell 0 and is "outside": alt = 255)
+        near_q[i] = near_fetch(px[i], py[i], rb[i], *lane_mh, lane_blob + lane_mh->off_fine, alt);   // (a NaN position reads cell 0 and is "outside": alt = 255)
         near_alt[i] = ((solid_bits >> i) & 1u) ? alt : 255u;
       }
     }
@@ -910,10 +988,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       for (int i = 0; i < PPL; ++i)
         if (((solid_bits >> i) & 1u) && near_decide(near_q[i], near_alt[i], rb[i])) near_bits |= 1u << i;
       if (__any_sync(0xffffffffu, near_bits != 0)) {
-        if (A.map_in_smem)
-          static_phase<PPL>(near_bits, t0, lane, A.mh, map_view(s_map, A.mh), poseA, poseB, hitmin, queue, qcount);
-        else
-          static_phase<PPL>(near_bits, t0, lane, A.mh, map_view(A.map_blob, A.mh), poseA, poseB, hitmin, queue, qcount);
+        static_phase<PPL, MAP_TABLE>(near_bits, t0, lane, tile * spw, mp_shift, A, s_map, poseA, poseB, hitmin, queue, qcount);
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
           const int h = hitmin[i * 32 + lane];
@@ -924,6 +999,13 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
 
     T2D_STAMP(6, hseg[0] + hseg[PPL - 1]);
     // ------------------------------------------------------------------ out of bound + flags
+    // the boundary box of this lane's scenario (Map.boundary of its tile)
+    float bxmin = A.bxmin, bxmax = A.bxmax, bymin = A.bymin, bymax = A.bymax;
+    bool has_bounds = A.has_bounds != 0;
+    if constexpr (MAP_TABLE) {
+      has_bounds = lane_mh->has_bounds != 0;
+      bxmin = lane_mh->bxmin; bxmax = lane_mh->bxmax; bymin = lane_mh->bymin; bymax = lane_mh->bymax;
+    }
     uint8_t fl[PPL];
     unsigned oob_check = 0;   // participants whose bounding circle is not well inside the box (rare): settled below, once
 #pragma unroll
@@ -933,14 +1015,14 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
       if (hseg[i] >= 0) f |= T2D_F_STATIC;
       // the bounding circle well inside the box: inside for sure (the common case)
       const float r = rb[i] * 1.0001f + 1e-3f;
-      const bool clear_in = (px[i] - A.bxmin > r) && (A.bxmax - px[i] > r) && (py[i] - A.bymin > r) && (A.bymax - py[i] > r);
-      if (A.has_bounds && ((solid_bits >> i) & 1u) && !clear_in) oob_check |= 1u << i;
+      const bool clear_in = (px[i] - bxmin > r) && (bxmax - px[i] > r) && (py[i] - bymin > r) && (bymax - py[i] > r);
+      if (has_bounds && ((solid_bits >> i) & 1u) && !clear_in) oob_check |= 1u << i;
       fl[i] = f;
     }
     if (oob_check) {
 #pragma unroll
       for (int i = 0; i < PPL; ++i)
-        if (((oob_check >> i) & 1u) && oob_slow(poseA, poseB, t0 + i, psh, A.bxmin, A.bxmax, A.bymin, A.bymax)) fl[i] |= T2D_F_OUTBOUND;
+        if (((oob_check >> i) & 1u) && oob_slow(poseA, poseB, t0 + i, psh, bxmin, bxmax, bymin, bymax)) fl[i] |= T2D_F_OUTBOUND;
     }
     if (nvalid == PPL && A.vec_ok) {
       int16_t h16[PPL], s16[PPL];
@@ -1205,7 +1287,8 @@ struct LidarArgs {
   const Params* table;
   int n_types;
   const unsigned char* map_blob;
-  MapHeader mh;
+  const uint32_t* tile_off;   // map table: byte offsets of the tiles; the scenario's tile id, or nullptr = tile 0 for all
+  const uint16_t* tile_id;
   const double* beam_cs;   // [n_beams][2] cos, sin of the beam angles (host float64)
   float* scan;             // [N][n_beams]
   int N, M, n_beams;
@@ -1245,8 +1328,11 @@ __global__ void __launch_bounds__(LIDAR_WARPS * 32, 7) t2d_lidar_kernel(const __
   sincos(th, &sa, &ca);
   const double xoff = -x0 * ca - y0 * sa, yoff = x0 * sa - y0 * ca;   // lidar.py:116-121
   const double R = A.range, R2 = R * R;
-  const float4* seg = A.map_blob ? reinterpret_cast<const float4*>(A.map_blob + A.mh.off_seg) : nullptr;
-  const int n_seg = A.map_blob ? A.mh.n_seg : 0;
+  // the scenario's static-geometry tile (its header is read from global memory: one warp, a handful of words)
+  const unsigned char* blob = A.map_blob ? A.map_blob + (A.tile_id ? A.tile_off[A.tile_id[n]] : 0u) : nullptr;
+  const MapHeader* tmh = reinterpret_cast<const MapHeader*>(blob);
+  const int n_seg = blob ? tmh->n_seg : 0;
+  const float4* seg = n_seg > 0 ? reinterpret_cast<const float4*>(blob + tmh->off_seg) : nullptr;
   const int part_rounds = (A.M - 1 + 31) / 32, seg_rounds = (n_seg + 31) / 32;
   for (int b0 = 0; b0 < A.n_beams; b0 += LIDAR_BEAMS) {
     const int nb = min(LIDAR_BEAMS, A.n_beams - b0);      // beams b0 .. b0 + nb - 1 in this pass
@@ -1633,7 +1719,10 @@ struct t2d_ctx {
   const float *reset_pool_wf = nullptr, *reset_pool_wr = nullptr;   // t2d_bind_reset_wheel_pool
   Params* d_table = nullptr;
   unsigned char* d_map = nullptr;
-  uint8_t* d_fine = nullptr;
+  uint32_t* d_tile_off = nullptr;   // [n_tiles] byte offsets of the tiles inside d_map
+  const uint16_t* tile_id = nullptr;   // caller-owned DEVICE [N] (more than one tile)
+  int n_tiles = 0;
+  bool has_segments = false;
   MapHeader mh{};
   int map_bytes = 0;
   bool has_bounds = false;
@@ -1657,6 +1746,7 @@ struct t2d_ctx {
   long long* dbg_clock = nullptr;
   int occ_smem[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per warps-per-CTA: smem the cached occupancy was computed for
   int occ_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int occ_variant[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // NPC controllers (t2d_set_controllers / t2d_set_paths / t2d_control)
   t2d_controller_params* d_ctab = nullptr;
   int n_ctrl = 0;
@@ -1707,13 +1797,8 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   c->device = device;
   c->N = n_scenarios;
   c->M = m_participants;
-  // participants per lane: 4 (measured on B200 at 4096 x 64: 28.6 us vs 37.1 us with 2 - the partner loop and
-  // the per-thread set-up amortise over more participants); T2D_PPL overrides for experiments
-  int ppl = 4;
-  if (const char* e = getenv("T2D_PPL")) {
-    const int v = atoi(e);
-    if ((v == 2 || v == 4) && 32 * v >= m_participants) ppl = v;   // the packed partner loop needs an even lane base
-  }
+  // participants per lane: 4 (2 was measured on B200 at 4096 x 64 in both rounds: 55 % more instructions, 21.5 vs 13.9 us)
+  const int ppl = 4;
   c->ppl = ppl;
   if (const char* e = getenv("T2D_PDL")) c->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("T2D_GRID_LIMIT")) c->grid_limit = std::max(0, atoi(e));
@@ -1739,7 +1824,7 @@ int t2d_destroy(t2d_ctx* c) {
   cudaSetDevice(c->device);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_map) cudaFree(c->d_map);
-  if (c->d_fine) cudaFree(c->d_fine);
+  if (c->d_tile_off) cudaFree(c->d_tile_off);
   if (c->d_ctab) cudaFree(c->d_ctab);
   if (c->d_path_v) cudaFree(c->d_path_v);
   if (c->d_path_off) cudaFree(c->d_path_off);
@@ -1818,28 +1903,49 @@ int t2d_set_type_table(t2d_ctx* c, const t2d_type_params* table, int n_types) {
   return T2D_OK;
 }
 
-// Host-side build of the static broadphase: a uniform grid over the segments' bounding box; each
-// cell lists (ascending) the segments whose axis-aligned box, grown by a small margin, touches it.
-int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bounds, float cell_size) {
-  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+// Host-side build of one static-geometry tile: the segments in list order (+ which of them close up to polygons), a
+// uniform grid over their bounding box grown by one cell, per cell the ascending list of the segments that touch it and
+// the "dilated" list of those within one cell of it, the clearance fields, the tile's boundary box.
+struct TileIn {
+  const float* segments; int n_seg;
+  const int32_t* poly_start; int n_poly;
+  const float* bounds;
+};
+
+static bool point_in_ring(const float* seg, int s0, int s1, double px, double py) {   // even-odd over the ring's edges
+  bool in = false;
+  for (int i = s0; i < s1; ++i) {
+    const double x1 = seg[4 * i], y1 = seg[4 * i + 1], x2 = seg[4 * i + 2], y2 = seg[4 * i + 3];
+    if ((y1 > py) != (y2 > py) && px < (x2 - x1) * (py - y1) / (y2 - y1) + x1) in = !in;
+  }
+  return in;
+}
+
+static int build_tile(const TileIn& t, float cell_size, std::vector<unsigned char>& blob) {
+  const float* segments = t.segments;
+  const int n_seg = t.n_seg;
   if (n_seg < 0 || n_seg > T2D_MAX_SEGMENTS) return fail(T2D_E_INVALID, "n_seg must be in 0..32767");
   if (n_seg > 0 && !segments) return fail(T2D_E_INVALID, "segments is NULL");
-  CUDA_TRY(cudaSetDevice(c->device));
-  c->has_bounds = bounds != nullptr;
-  if (bounds) {
-    if (!(bounds[0] <= bounds[1] && bounds[2] <= bounds[3])) return fail(T2D_E_INVALID, "bounds must be (xmin<=xmax, ymin<=ymax)");
-    memcpy(c->bounds, bounds, sizeof(float) * 4);
+  if (t.n_poly < 0 || (t.n_poly > 0 && !t.poly_start)) return fail(T2D_E_INVALID, "poly_start is NULL");
+  if (t.bounds && !(t.bounds[0] <= t.bounds[1] && t.bounds[2] <= t.bounds[3])) return fail(T2D_E_INVALID, "bounds must be (xmin<=xmax, ymin<=ymax)");
+  for (int p = 0; p < t.n_poly; ++p) {
+    const int s0 = t.poly_start[p], s1 = t.poly_start[p + 1];
+    if (s0 < 0 || s1 > n_seg || s1 - s0 < 3 || (p > 0 && s0 < t.poly_start[p])) return fail(T2D_E_INVALID, "poly_start: rings must be ascending, inside the segment list and have >= 3 edges");
+    for (int i = s0; i < s1; ++i) {   // a ring: every edge ends where the next one starts, the last one at the first one's start
+      const int j = i + 1 < s1 ? i + 1 : s0;
+      if (segments[4 * i + 2] != segments[4 * j] || segments[4 * i + 3] != segments[4 * j + 1]) return fail(T2D_E_INVALID, "poly_start: a ring's edges must chain and close");
+    }
   }
-  if (c->d_map) {
-    cudaFree(c->d_map);
-    c->d_map = nullptr;
+  MapHeader mh{};
+  mh.n_seg = n_seg; mh.n_poly = t.n_poly;
+  mh.has_bounds = t.bounds ? 1 : 0;
+  if (t.bounds) { mh.bxmin = t.bounds[0]; mh.bxmax = t.bounds[1]; mh.bymin = t.bounds[2]; mh.bymax = t.bounds[3]; }
+  if (n_seg == 0) {   // bounds only
+    mh.gx = mh.gy = 0; mh.total_bytes = mh.smem_bytes = mh.off_fine = sizeof(MapHeader);
+    blob.assign(sizeof(MapHeader), 0);
+    memcpy(blob.data(), &mh, sizeof(mh));
+    return T2D_OK;
   }
-  if (c->d_fine) {
-    cudaFree(c->d_fine);
-    c->d_fine = nullptr;
-  }
-  c->map_bytes = 0;
-  if (n_seg == 0) return T2D_OK;
   float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
   for (int i = 0; i < n_seg * 4; ++i)
     if (!std::isfinite(segments[i])) return fail(T2D_E_INVALID, "segments must be finite");
@@ -1891,8 +1997,9 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   size_t n_items = 0, n_ditems = 0;
   for (auto& v : cells) n_items += v.size();
   for (auto& v : dcells) n_ditems += v.size();
-  MapHeader mh{};
-  mh.n_seg = n_seg; mh.gx = gx; mh.gy = gy; mh.n_items = (int)n_items; mh.n_ditems = (int)n_ditems;
+  int fine = 4;   // bounded host work: cells x segments <= ~1e8 distance evaluations
+  while (fine > 1 && (double)gx * gy * fine * fine * n_seg > 1e8) fine >>= 1;
+  mh.gx = gx; mh.gy = gy; mh.n_items = (int)n_items; mh.n_ditems = (int)n_ditems; mh.fine = fine;
   mh.x0 = x0; mh.y0 = y0; mh.inv_cell = inv; mh.cell = cell; mh.dil = dil;
   auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
   mh.off_seg = (uint32_t)up16(sizeof(MapHeader));
@@ -1900,9 +2007,14 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   mh.off_items = (uint32_t)up16(mh.off_cell + ((size_t)gx * gy + 1) * 4);
   mh.off_dcell = (uint32_t)up16(mh.off_items + n_items * 2);
   mh.off_ditems = (uint32_t)up16(mh.off_dcell + ((size_t)gx * gy + 1) * 4);
-  mh.off_clear = (uint32_t)up16(mh.off_ditems + n_ditems * 2);
-  mh.total_bytes = (uint32_t)up16(mh.off_clear + (size_t)gx * gy * 4);
-  std::vector<unsigned char> blob(mh.total_bytes, 0);
+  mh.off_objfirst = (uint32_t)up16(mh.off_ditems + n_ditems * 2);
+  mh.off_poly = (uint32_t)up16(mh.off_objfirst + (size_t)n_seg * 2);
+  mh.off_pbox = (uint32_t)up16(mh.off_poly + ((size_t)t.n_poly + 1) * 4);
+  mh.off_clear = (uint32_t)up16(mh.off_pbox + (size_t)t.n_poly * 16);
+  mh.off_fine = (uint32_t)up16(mh.off_clear + (size_t)gx * gy * 4);
+  mh.smem_bytes = mh.off_fine;   // the fine field is read through L1 / L2, everything in front of it may be staged
+  mh.total_bytes = (uint32_t)up16(mh.off_fine + (size_t)gx * fine * gy * fine);
+  blob.assign(mh.total_bytes, 0);
   memcpy(blob.data(), &mh, sizeof(mh));
   memcpy(blob.data() + mh.off_seg, segments, (size_t)n_seg * 16);
   auto write_lists = [&](const std::vector<std::vector<uint16_t>>& lists, uint32_t off_start, uint32_t off_items) {
@@ -1917,18 +2029,41 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
   };
   write_lists(cells, mh.off_cell, mh.off_items);
   write_lists(dcells, mh.off_dcell, mh.off_ditems);
+  // the object a segment belongs to, named by the object's first segment: an open polyline piece is its own object, the
+  // edges of a polygon share the polygon's first edge (StaticCollision.update reports the first OBJECT hit, collision.py:37-43)
+  uint16_t* objfirst = reinterpret_cast<uint16_t*>(blob.data() + mh.off_objfirst);
+  for (int i = 0; i < n_seg; ++i) objfirst[i] = (uint16_t)i;
+  int32_t* pstart = reinterpret_cast<int32_t*>(blob.data() + mh.off_poly);
+  float* pbox = reinterpret_cast<float*>(blob.data() + mh.off_pbox);
+  for (int p = 0; p < t.n_poly; ++p) {
+    const int s0 = t.poly_start[p], s1 = t.poly_start[p + 1];
+    pstart[p] = s0;
+    float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+    for (int i = s0; i < s1; ++i) {
+      objfirst[i] = (uint16_t)s0;
+      bx0 = std::min(bx0, segments[4 * i]); bx1 = std::max(bx1, segments[4 * i]);
+      by0 = std::min(by0, segments[4 * i + 1]); by1 = std::max(by1, segments[4 * i + 1]);
+    }
+    pbox[4 * p] = bx0; pbox[4 * p + 1] = bx1; pbox[4 * p + 2] = by0; pbox[4 * p + 3] = by1;
+  }
+  pstart[t.n_poly] = t.n_poly > 0 ? t.poly_start[t.n_poly] : 0;
   // clearance fields: lower bound of the distance from any point of a cell to the nearest segment
-  // (distance from the cell centre minus the half diagonal).  Coarse (float, in the blob) and fine
-  // (bytes of CLEAR_QUANT metres, 4 x 4 per coarse cell, in global memory).
+  // (distance from the cell centre minus the half diagonal); ZERO inside a polygon - a pose deep inside an obstacle
+  // touches no edge but intersects the Area all the same.  Coarse (float per cell) and fine (bytes of CLEAR_QUANT metres,
+  // fine x fine per coarse cell, read through L1 / L2).
   auto centre_dist = [&](double px, double py) {
+    for (int p = 0; p < t.n_poly; ++p)
+      if (px >= pbox[4 * p] && px <= pbox[4 * p + 1] && py >= pbox[4 * p + 2] && py <= pbox[4 * p + 3] &&
+          point_in_ring(segments, t.poly_start[p], t.poly_start[p + 1], px, py))
+        return 0.0;
     double best = INFINITY;
     for (int i = 0; i < n_seg; ++i) {
       const float* sg = segments + 4 * i;
       const double dx = (double)sg[2] - sg[0], dy = (double)sg[3] - sg[1], ux = px - sg[0], uy = py - sg[1];
       const double dd = dx * dx + dy * dy;
-      double t = dd > 0.0 ? (ux * dx + uy * dy) / dd : 0.0;
-      t = std::min(1.0, std::max(0.0, t));
-      const double ex = ux - t * dx, ey = uy - t * dy;
+      double tt = dd > 0.0 ? (ux * dx + uy * dy) / dd : 0.0;
+      tt = std::min(1.0, std::max(0.0, tt));
+      const double ex = ux - tt * dx, ey = uy - tt * dy;
       best = std::min(best, ex * ex + ey * ey);
     }
     return std::sqrt(best);
@@ -1942,11 +2077,7 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
         clr[(size_t)cy * gx + cx] = d > 0.0 ? (float)(d * 0.9999) : 0.0f;
       }
   }
-  int fine = 4;   // bounded host work: cells x segments <= ~1e8 distance evaluations
-  while (fine > 1 && (double)gx * gy * fine * fine * n_seg > 1e8) fine >>= 1;
-  mh.fine = fine;
-  memcpy(blob.data(), &mh, sizeof(mh));
-  std::vector<uint8_t> fine_field((size_t)gx * fine * gy * fine);
+  uint8_t* fine_field = blob.data() + mh.off_fine;
   {
     const double fc = (double)cell / fine;
     const double half_diag = 0.5 * std::sqrt(2.0) * fc * 1.001 + 2.0 * margin + 1e-3 * fc;
@@ -1957,13 +2088,56 @@ int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bound
         fine_field[(size_t)iy * gx * fine + ix] = (uint8_t)std::min(255.0, q);
       }
   }
-  CUDA_TRY(cudaMalloc(&c->d_fine, fine_field.size()));
-  CUDA_TRY(cudaMemcpy(c->d_fine, fine_field.data(), fine_field.size(), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&c->d_map, mh.total_bytes));
-  CUDA_TRY(cudaMemcpy(c->d_map, blob.data(), mh.total_bytes, cudaMemcpyHostToDevice));
-  c->map_bytes = (int)mh.total_bytes;
-  c->mh = mh;
   return T2D_OK;
+}
+
+int t2d_set_map_table(t2d_ctx* c, const t2d_map_tile* tiles, int n_tiles, const uint16_t* tile_id, float cell_size) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (n_tiles < 0 || n_tiles > T2D_MAX_TILES) return fail(T2D_E_INVALID, "n_tiles must be in 0..T2D_MAX_TILES");
+  if (n_tiles > 0 && !tiles) return fail(T2D_E_INVALID, "tiles is NULL");
+  if (n_tiles > 1 && !tile_id) return fail(T2D_E_INVALID, "tile_id is NULL (needed with more than one tile)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->d_map) { cudaFree(c->d_map); c->d_map = nullptr; }
+  if (c->d_tile_off) { cudaFree(c->d_tile_off); c->d_tile_off = nullptr; }
+  c->map_bytes = 0; c->n_tiles = 0; c->tile_id = nullptr; c->has_bounds = false; c->has_segments = false;
+  c->mh = MapHeader{};
+  if (n_tiles == 0) return T2D_OK;
+  std::vector<unsigned char> all;
+  std::vector<uint32_t> offs((size_t)n_tiles);
+  bool any_bounds = false, any_seg = false;
+  for (int i = 0; i < n_tiles; ++i) {
+    TileIn t{tiles[i].segments, tiles[i].n_seg, tiles[i].poly_start, tiles[i].n_poly, tiles[i].bounds};
+    std::vector<unsigned char> blob;
+    if (int r = build_tile(t, cell_size, blob)) return r;
+    offs[i] = (uint32_t)all.size();
+    all.insert(all.end(), blob.begin(), blob.end());
+    all.resize((all.size() + 127) / 128 * 128, 0);   // every tile starts 128-byte aligned
+    any_bounds = any_bounds || tiles[i].bounds != nullptr;
+    any_seg = any_seg || tiles[i].n_seg > 0;
+    if (i == 0) memcpy(&c->mh, blob.data(), sizeof(MapHeader));
+  }
+  CUDA_TRY(cudaMalloc(&c->d_map, all.size()));
+  CUDA_TRY(cudaMemcpy(c->d_map, all.data(), all.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&c->d_tile_off, sizeof(uint32_t) * (size_t)n_tiles));
+  CUDA_TRY(cudaMemcpy(c->d_tile_off, offs.data(), sizeof(uint32_t) * (size_t)n_tiles, cudaMemcpyHostToDevice));
+  c->n_tiles = n_tiles;
+  c->tile_id = n_tiles > 1 ? tile_id : nullptr;
+  c->map_bytes = (int)c->mh.smem_bytes;     // what a single tile stages into shared memory
+  c->has_bounds = any_bounds; c->has_segments = any_seg;
+  if (c->mh.has_bounds) { c->bounds[0] = c->mh.bxmin; c->bounds[1] = c->mh.bxmax; c->bounds[2] = c->mh.bymin; c->bounds[3] = c->mh.bymax; }
+  return T2D_OK;
+}
+
+int t2d_set_map_polygons(t2d_ctx* c, const float* segments, int n_seg, const int32_t* poly_start, int n_poly, const float* bounds,
+                         float cell_size) {
+  if (n_seg == 0 && !bounds) return t2d_set_map_table(c, nullptr, 0, nullptr, cell_size);
+  t2d_map_tile t{};
+  t.segments = segments; t.n_seg = n_seg; t.poly_start = poly_start; t.n_poly = n_poly; t.bounds = bounds;
+  return t2d_set_map_table(c, &t, 1, nullptr, cell_size);
+}
+
+int t2d_set_map(t2d_ctx* c, const float* segments, int n_seg, const float* bounds, float cell_size) {
+  return t2d_set_map_polygons(c, segments, n_seg, nullptr, 0, bounds, cell_size);
 }
 
 int t2d_bind_state(t2d_ctx* c, float* x, float* y, float* heading, float* speed, float* vx, float* vy,
@@ -2031,8 +2205,10 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.wheel_f = c->wheel_f ? c->wheel_f + p0 : nullptr; A.wheel_r = c->wheel_r ? c->wheel_r + p0 : nullptr;
   A.action = action; A.ego_action = c->ego_action ? c->ego_action + 2 * (size_t)first : nullptr; A.flags = flags; A.hit_index = hit_index; A.hit_segment = hit_segment;
   A.scn_status = scn_status; A.done = done;
-  A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.map_fine = c->d_fine; A.mh = c->mh;
-  A.map_in_smem = (c->d_map && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
+  const bool map_table = c->n_tiles > 1;
+  A.map_blob = c->d_map; A.map_bytes = c->map_bytes; A.mh = c->mh;
+  A.tile_off = c->d_tile_off; A.tile_id = map_table ? c->tile_id + first : nullptr;
+  A.map_in_smem = (!map_table && c->d_map && c->mh.n_seg > 0 && c->map_bytes <= MAP_SMEM_LIMIT) ? 1 : 0;
   A.table = c->d_table; A.n_types = c->n_types;
   A.N = count; A.M = c->M; A.G = c->G;
   const int delta_t = std::min(c->cfg.delta_t_ms, c->cfg.interval_ms);
@@ -2087,14 +2263,12 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   if (smem > c->max_smem_optin) return fail(T2D_E_UNSUPPORTED, "shared memory budget exceeded");
   using kernel_t = void (*)(StepArgs);
   kernel_t kern;
-  if (c->kin_only)
-    kern = c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, true> : (kernel_t)t2d_step_kernel<4, true>;
-  else
-    kern = c->ppl == 2 ? (kernel_t)t2d_step_kernel<2, false> : (kernel_t)t2d_step_kernel<4, false>;
+  if (c->kin_only) kern = map_table ? (kernel_t)t2d_step_kernel<4, true, true> : (kernel_t)t2d_step_kernel<4, true, false>;
+  else kern = map_table ? (kernel_t)t2d_step_kernel<4, false, true> : (kernel_t)t2d_step_kernel<4, false, false>;
   {
     // cudaFuncSetAttribute applies to the kernel function for the whole process and SETS the value: worlds of
     // different sizes share it, so the opt-in is tracked per (device, kernel variant) and only ever raised.
-    const int variant = (c->kin_only ? 2 : 0) + (c->ppl == 2 ? 1 : 0);
+    const int variant = (c->kin_only ? 2 : 0) + (map_table ? 1 : 0);
     std::lock_guard<std::mutex> lock(g_smem_mutex);
     int& configured = g_smem_configured[c->device % 64][variant];
     if (smem > configured) {
@@ -2110,11 +2284,12 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
     CUDA_TRY(cudaGetLastError());
   }
   const long long ctas_needed = (tiles + wpc - 1) / wpc;
-  if (c->occ_smem[wpc] != smem) {
+  if (c->occ_smem[wpc] != smem || c->occ_variant[wpc] != (map_table ? 1 : 0)) {
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     c->occ_val[wpc] = per_sm < 1 ? 1 : per_sm;
     c->occ_smem[wpc] = smem;
+    c->occ_variant[wpc] = map_table ? 1 : 0;
   }
   int per_sm_ctas = c->occ_val[wpc];
   if (c->grid_limit > 0) per_sm_ctas = std::min(per_sm_ctas, c->grid_limit);   // T2D_GRID_LIMIT: leave CTA slots to other streams
@@ -2313,7 +2488,8 @@ int t2d_lidar_scan(t2d_ctx* c, int n_beams, float max_range, const double* beam_
   CUDA_TRY(cudaSetDevice(c->device));
   LidarArgs A{};
   A.x = c->x; A.y = c->y; A.h = c->h; A.type_id = c->type_id; A.table = c->d_table; A.n_types = c->n_types;
-  A.map_blob = c->d_map; A.mh = c->mh; A.beam_cs = beam_cos_sin; A.scan = scan;
+  A.map_blob = c->d_map; A.tile_off = c->d_tile_off; A.tile_id = c->n_tiles > 1 ? c->tile_id : nullptr;
+  A.beam_cs = beam_cos_sin; A.scan = scan;
   A.N = c->N; A.M = c->M; A.n_beams = n_beams; A.range = (double)max_range;
   const int grid = (c->N + LIDAR_WARPS - 1) / LIDAR_WARPS;
   t2d_lidar_kernel<<<grid, LIDAR_WARPS * 32, 0, (cudaStream_t)stream>>>(A);

@@ -127,3 +127,28 @@ def load_collidable_segments(name: str):
 
 def list_tiles() -> List[str]:
     return sorted(f[:-4] for f in os.listdir(TILE_DIR) if f.endswith(".npz")) if os.path.isdir(TILE_DIR) else []
+
+
+def polygons_to_segments(polygons, polylines=()):
+    """Flatten static objects into the tile format of ``BatchedWorld.set_map`` / ``set_map_table``.
+
+    ``polygons``: list of [V, 2] vertex arrays (``Area.geometry.exterior`` without the repeated closing vertex), in the
+    order ``StaticCollision.reset`` receives the areas; ``polylines``: list of [V, 2] arrays (``RoadLine.geometry``), appended
+    after them.  Returns ``(segments [S, 4] float32, poly_start [P + 1] int32)``: ring p = segments
+    [poly_start[p], poly_start[p + 1]), each edge ending exactly where the next one starts."""
+    segs, starts = [], [0]
+    for poly in polygons:
+        v = np.asarray(poly, dtype=np.float32).reshape(-1, 2)
+        if len(v) >= 2 and np.array_equal(v[0], v[-1]):
+            v = v[:-1]
+        if len(v) < 3:
+            raise ValueError("a polygon needs at least 3 vertices")
+        nxt = np.roll(v, -1, axis=0)
+        segs.append(np.concatenate([v, nxt], 1))
+        starts.append(starts[-1] + len(v))
+    for line in polylines:
+        v = np.asarray(line, dtype=np.float32).reshape(-1, 2)
+        if len(v) >= 2:
+            segs.append(np.concatenate([v[:-1], v[1:]], 1))
+    seg = np.concatenate(segs, 0).astype(np.float32) if segs else np.zeros((0, 4), np.float32)
+    return np.ascontiguousarray(seg), np.asarray(starts, dtype=np.int32)

@@ -102,6 +102,8 @@ class BatchedWorld:
             self.omega_rear = torch.zeros(shape, **f)
             _lib.check(self.lib.t2d_bind_wheel_state(self._ctx, _ptr(self.omega_front), _ptr(self.omega_rear)))
         self.segments = None
+        self.poly_start = None
+        self.tiles, self.tile_id = None, None
         self.bounds = None
         self._goal = None
 
@@ -135,21 +137,56 @@ class BatchedWorld:
         cfg = _lib.Config(self.interval, self.delta_t, self.max_step, self.flags_cfg)
         _lib.check(self.lib.t2d_set_config(self._ctx, C.byref(cfg)))
 
-    def set_map(self, segments=None, bounds: Optional[Sequence[float]] = None, cell_size: float = 0.0):
+    def set_map(self, segments=None, bounds: Optional[Sequence[float]] = None, cell_size: float = 0.0, poly_start=None):
         """Static geometry of the scenario (shared by all N scenarios).
 
-        ``segments``: array [S, 4] of (x1, y1, x2, y2) collidable polyline pieces in list order -
-        what ``StaticCollision.reset(static_objects)`` receives (collision.py:45-46), flattened;
+        ``segments``: array [S, 4] of (x1, y1, x2, y2) collidable pieces in list order - what
+        ``StaticCollision.reset(static_objects)`` receives (collision.py:45-46), flattened;
         ``bounds``: (xmin, xmax, ymin, ymax) as ``Map.boundary`` / ``OutBound.reset`` take it
-        (out_bound.py:50-65), or None."""
+        (out_bound.py:50-65), or None;
+        ``poly_start``: int array [P + 1] marking the segments that close up to ``Area`` polygons (ring p = segments
+        [poly_start[p], poly_start[p + 1])): a pose inside a polygon collides with it even when it touches no edge, and
+        ``hit_segment`` then names the first object hit by its first segment (see :func:`polygons_to_segments`)."""
         seg = None if segments is None else np.ascontiguousarray(np.asarray(segments, dtype=np.float32).reshape(-1, 4))
         n_seg = 0 if seg is None else seg.shape[0]
-        b = None if bounds is None else np.asarray(bounds, dtype=np.float32)
-        _lib.check(self.lib.t2d_set_map(
-            self._ctx, C.c_void_p(0 if n_seg == 0 else seg.ctypes.data), n_seg,
-            C.c_void_p(0 if b is None else b.ctypes.data), float(cell_size)))
+        b = None if bounds is None else np.ascontiguousarray(np.asarray(bounds, dtype=np.float32))
+        ps = None if poly_start is None else np.ascontiguousarray(np.asarray(poly_start, dtype=np.int32))
+        n_poly = 0 if ps is None else len(ps) - 1
+        _lib.check(self.lib.t2d_set_map_polygons(
+            self._ctx, C.c_void_p(0 if n_seg == 0 else seg.ctypes.data), n_seg, C.c_void_p(0 if n_poly <= 0 else ps.ctypes.data),
+            max(0, n_poly), C.c_void_p(0 if b is None else b.ctypes.data), float(cell_size)))
         self.segments = seg
+        self.poly_start = ps
         self.bounds = None if b is None else tuple(float(v) for v in b)
+        self.tiles, self.tile_id = None, None
+
+    def set_map_table(self, tiles, tile_id, cell_size: float = 0.0):
+        """A different map per scenario: ``tiles`` is a list of dicts ``{"segments": [S, 4], "bounds": (4,) or None,
+        "poly_start": [P + 1] or None}`` (what ``_ParkingScenarioManager.reset`` builds per episode - the lot's wall and
+        obstacle Areas and ``map_.boundary``, envs/parking.py:397-441 - or the reference's ``data/*_map`` files, one tile
+        each), ``tile_id`` an integer array [N]: the tile of every scenario.  The ids live in ``self.tile_id`` (uint16
+        device tensor) and may be rewritten between ticks."""
+        keep, rows = [], (_lib.MapTileC * len(tiles))()
+        for i, t in enumerate(tiles):
+            seg = t.get("segments")
+            seg = None if seg is None or len(seg) == 0 else np.ascontiguousarray(np.asarray(seg, dtype=np.float32).reshape(-1, 4))
+            b = t.get("bounds")
+            b = None if b is None else np.ascontiguousarray(np.asarray(b, dtype=np.float32))
+            ps = t.get("poly_start")
+            ps = None if ps is None or len(ps) < 2 else np.ascontiguousarray(np.asarray(ps, dtype=np.int32))
+            keep.append((seg, b, ps))
+            rows[i].segments = None if seg is None else seg.ctypes.data
+            rows[i].n_seg = 0 if seg is None else seg.shape[0]
+            rows[i].poly_start = None if ps is None else ps.ctypes.data
+            rows[i].n_poly = 0 if ps is None else len(ps) - 1
+            rows[i].bounds = None if b is None else b.ctypes.data
+        tid = torch.as_tensor(np.asarray(tile_id) if not torch.is_tensor(tile_id) else tile_id).to(torch.int64)
+        if tid.numel() != self.N or int(tid.min()) < 0 or int(tid.max()) >= len(tiles):
+            raise ValueError(f"tile_id must hold {self.N} indices into the {len(tiles)} tiles")
+        self.tile_id = tid.to(torch.int16).to(self.device).contiguous()   # (bit pattern of uint16 for ids < 32768)
+        _lib.check(self.lib.t2d_set_map_table(self._ctx, rows, len(tiles), _ptr(self.tile_id), float(cell_size)))
+        self.tiles = [dict(segments=k[0], bounds=None if k[1] is None else tuple(float(v) for v in k[1]), poly_start=k[2]) for k in keep]
+        self.segments, self.poly_start, self.bounds = None, None, None
 
     def set_goal(self, target=None, arrival_threshold: float = 0.95, no_action_max_step: int = 100):
         """Target area per scenario for the ego (participant 0): array [N, 5] = (cx, cy, heading, half_len, half_wid),

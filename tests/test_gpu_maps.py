@@ -1,0 +1,143 @@
+"""Static objects that are Area polygons (containment counts) and a different map per scenario (t2d_set_map_polygons /
+t2d_set_map_table), against the float64 oracle: flags, first-hit object and status bit-exact."""
+
+import numpy as np
+import pytest
+
+from oracle import scenario as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _parking_like_objects():
+    """Walls and obstacles the way ParkingLotGenerator builds them (map/generator/generate_parking_lot.py:122-205,354-385):
+    Area polygons - a long wall, a block big enough to swallow a car, an L-shaped (concave) obstacle, a kerb stone smaller
+    than a car - plus an open kerb line."""
+    from tactics2d_b200.map import polygons_to_segments
+
+    polys = [
+        [(-30, 18), (30, 18), (30, 19), (-30, 19)],                          # wall
+        [(-25, -20), (-5, -20), (-5, -4), (-25, -4)],                        # block: a car fits inside
+        [(4, -18), (16, -18), (16, -6), (12, -6), (12, -14), (4, -14)],      # L shape: its notch is outside the polygon
+        [(20.0, 5.0), (20.8, 5.0), (20.8, 5.4), (20.0, 5.4)],                # smaller than a car
+    ]
+    lines = [[(-30, -26), (0, -27), (30, -26)]]
+    return polygons_to_segments(polys, lines)
+
+
+def test_polygon_obstacles_containment_and_first_object(cuda_device):
+    import torch
+
+    from tactics2d_b200 import BatchedWorld, synthetic
+
+    seg, ps = _parking_like_objects()
+    bounds = (-40.0, 40.0, -40.0, 40.0)
+    n, m = 96, 16
+    scene = synthetic.config2(n, m, seed=41, size=70.0)
+    x = scene.x - 35.0
+    y = scene.y - 35.0
+    # hand-placed cases in scenario 0: deep inside the block (no edge in reach), inside the L's notch (inside its bounding
+    # box, outside the polygon), on top of the small kerb stone (polygon inside the pose), straddling the wall, far away
+    x[0, :5] = (-15.0, 8.0, 20.4, 0.0, 33.0)
+    y[0, :5] = (-12.0, -10.0, 5.2, 18.5, 33.0)
+    table = scene.table.as_oracle_table()
+    w = BatchedWorld(n, m, scene.table, device=cuda_device, any_participant=True)
+    w.set_map(seg, bounds, poly_start=ps)
+    w.set_state(x, y, scene.heading, scene.speed, type_id=scene.type_id)
+    r = w.check_events()
+    torch.cuda.synchronize()
+    fl, hi, hs = O.events(x, y, scene.heading, scene.type_id, table, seg, bounds, poly_start=ps)
+    assert np.array_equal(r.flags.cpu().numpy(), fl)
+    assert np.array_equal(r.hit_segment.cpu().numpy(), hs)
+    assert np.array_equal(r.hit_index.cpu().numpy(), hi)
+    # the hand-placed cases say what they were built to say
+    assert hs[0, 0] == 4 and (fl[0, 0] & 2)          # wholly inside the block: object = its first segment
+    assert hs[0, 1] == -1 and not (fl[0, 1] & 2)     # the notch of the L is free space
+    assert hs[0, 2] == 14 and (fl[0, 2] & 2)         # the kerb stone under the car
+    assert hs[0, 3] == 0 and (fl[0, 3] & 2)          # the wall
+    assert hs[0, 4] == -1
+    inside_only = 0
+    plain = O.events(x, y, scene.heading, scene.type_id, table, seg, bounds)[0]
+    inside_only = int((((fl & 2) != 0) & ((plain & 2) == 0)).sum())
+    assert inside_only >= 10    # poses that only the containment rule catches
+    # a few ticks: physics + events + status on the moving poses
+    for t in range(3):
+        act = torch.from_numpy(synthetic.random_actions(4100 + t, (n, m))).to(cuda_device)
+        r = w.step(act)
+        torch.cuda.synchronize()
+        got = w.state_numpy()
+        fl, hi, hs = O.events(got["x"], got["y"], got["heading"], scene.type_id, table, seg, bounds, poly_start=ps)
+        assert np.array_equal(r.flags.cpu().numpy(), fl) and np.array_equal(r.hit_segment.cpu().numpy(), hs)
+        st, done = O.status(fl, scene.type_id, np.full(n, t + 1), 0, ego_only=False)
+        assert np.array_equal(r.status.cpu().numpy(), st)
+    w.close()
+
+
+def test_map_table_one_tile_per_scenario(cuda_device):
+    """configs[2] says "highD_map tiles": highD_1 .. highD_6 in ONE batch, every scenario on its own tile (segments and
+    boundary box), plus a tile of polygons and an empty tile; tile ids rewritten between ticks."""
+    import torch
+
+    from tactics2d_b200 import BatchedWorld, synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    tiles = []
+    for k in range(1, 7):
+        seg, bounds = load_collidable_segments(f"highD_{k}")
+        tiles.append(dict(segments=seg, bounds=bounds, poly_start=None))
+    pseg, ps = _parking_like_objects()
+    tiles.append(dict(segments=pseg, bounds=(-40.0, 40.0, -40.0, 40.0), poly_start=ps))
+    tiles.append(dict(segments=None, bounds=(0.0, 100.0, -50.0, 50.0), poly_start=None))       # bounds only
+    n, m = 64, 32
+    rng = np.random.default_rng(5)
+    tile_id = rng.integers(0, len(tiles), n)
+    tile_id[:8] = np.arange(8)
+    scene = synthetic.config3(n, m, seed=43, segments=None, bounds=tiles[0]["bounds"])
+    x, y = scene.x.copy(), scene.y.copy()
+    for s in range(n):
+        b = tiles[tile_id[s]]["bounds"]
+        x[s] = rng.uniform(b[0] - 3, b[1] + 3, m)
+        y[s] = rng.uniform(b[2] - 3, b[3] + 3, m)
+    table = scene.table.as_oracle_table()
+    w = BatchedWorld(n, m, scene.table, device=cuda_device, any_participant=True)
+    w.set_map_table(tiles, tile_id)
+    w.set_state(x, y, scene.heading, scene.speed, type_id=scene.type_id)
+
+    def check(r, xs, ys, hs_, ids):
+        gfl, ghs, ghi = r.flags.cpu().numpy(), r.hit_segment.cpu().numpy(), r.hit_index.cpu().numpy()
+        n_static = 0
+        for s in range(n):
+            t = tiles[ids[s]]
+            fl, hi, hs = O.events(xs[s:s + 1], ys[s:s + 1], hs_[s:s + 1], scene.type_id[s:s + 1], table, t["segments"], t["bounds"],
+                                  poly_start=t["poly_start"])
+            assert np.array_equal(gfl[s], fl[0]), (s, ids[s])
+            assert np.array_equal(ghs[s], hs[0]) and np.array_equal(ghi[s], hi[0]), (s, ids[s])
+            n_static += int(((fl & 2) != 0).sum())
+        return n_static
+
+    r = w.check_events()
+    torch.cuda.synchronize()
+    assert check(r, x, y, scene.heading, tile_id) > 20
+    for t in range(2):
+        act = torch.from_numpy(synthetic.random_actions(4300 + t, (n, m), accel=(-6, 3), steer=(-0.05, 0.05))).to(cuda_device)
+        r = w.step(act)
+        torch.cuda.synchronize()
+        got = w.state_numpy()
+        check(r, got["x"], got["y"], got["heading"], tile_id)
+    # a reset that draws new maps rewrites the ids in place: the next tick uses them
+    new_ids = (tile_id + 3) % len(tiles)
+    w.tile_id.copy_(torch.from_numpy(new_ids.astype(np.int16)))
+    r = w.check_events()
+    torch.cuda.synchronize()
+    got = w.state_numpy()
+    check(r, got["x"], got["y"], got["heading"], new_ids)
+    # the lidar of a scenario sees its own tile's segments
+    scan = w.lidar_scan(72, 30.0).cpu().numpy()
+    for s in (0, 6, 7):
+        t = tiles[new_ids[s]]
+        w1 = BatchedWorld(1, m, scene.table, device=cuda_device)
+        w1.set_map(t["segments"], t["bounds"], poly_start=t["poly_start"])
+        w1.set_state(got["x"][s:s + 1], got["y"][s:s + 1], got["heading"][s:s + 1], got["speed"][s:s + 1], type_id=scene.type_id[s:s + 1])
+        assert np.array_equal(w1.lidar_scan(72, 30.0).cpu().numpy()[0], scan[s])
+        w1.close()
+    w.close()
