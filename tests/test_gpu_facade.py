@@ -190,6 +190,63 @@ def test_detectors_and_scenario_manager(cuda_device):
     w.close()
 
 
+def test_detectors_take_one_pose_like_the_reference(cuda_device):
+    """The reference's call form: ``detector.update(agent_pose)`` with ONE pose (collision.py:18-25,37-43, out_bound.py:37-48,
+    arrival.py:32-47) - here the (4, 2) ring of ``Vehicle.get_pose()`` - returns ONE bool, computed by the same kernels."""
+    from oracle import geometry as G
+    from tactics2d_b200.map import polygons_to_segments
+    from tactics2d_b200.participant.element import Vehicle
+    from tactics2d_b200.participant.trajectory import State
+    from tactics2d_b200.traffic.event_detection import Arrival, DynamicCollision, OutBound, StaticCollision
+
+    def car(x, y, heading, id_=0):
+        v = Vehicle(id_=id_)
+        v.load_from_template("medium_car")
+        v.add_state(State(frame=0, x=x, y=y, heading=heading, speed=0.0))
+        return v
+
+    seg, ps = polygons_to_segments([[(-20, -10), (-4, -10), (-4, 4), (-20, 4)]], [[(10, -5), (10, 5)]])
+    sc = StaticCollision()
+    sc.reset(seg, poly_start=ps)
+    ob = OutBound((-30.0, 30.0, -30.0, 30.0))
+    dc = DynamicCollision()
+    rng = np.random.default_rng(3)
+    n_hit = n_out = n_dyn = 0
+    for k in range(40):
+        x, y, h = rng.uniform(-32, 32), rng.uniform(-32, 32), rng.uniform(0, 6.28)
+        if k == 0:
+            x, y, h = -12.0, -3.0, 0.3          # wholly inside the polygon
+        ego = car(x, y, h)
+        pose = ego.get_pose()
+        hl, hw = ego.length / 2, ego.width / 2
+        c, s_ = np.cos(np.float32(h).astype(np.float64)), np.sin(np.float32(h).astype(np.float64))
+        xf, yf = float(np.float32(x)), float(np.float32(y))
+        edge = bool(np.any(G.obb_segment(xf, yf, c, s_, np.float32(hl), np.float32(hw), *(seg[:, i].astype(np.float64) for i in range(4)))))
+        inside = bool(G.point_in_ring(np.array([xf]), np.array([yf]), seg[:4])[0])
+        assert sc.update(pose) == (edge or inside), k
+        ex, ey = G.extents(c, s_, np.float64(np.float32(hl)), np.float64(np.float32(hw)))
+        assert ob.update(pose) == bool(G.out_of_bound(xf, yf, ex, ey, (-30.0, 30.0, -30.0, 30.0))), k
+        others = [car(x + rng.uniform(-6, 6), y + rng.uniform(-6, 6), rng.uniform(0, 6.28), id_=j + 1) for j in range(3)]
+        want = False
+        for o in others:
+            so = o.current_state
+            oc, os_ = np.cos(np.float64(np.float32(so.heading))), np.sin(np.float64(np.float32(so.heading)))
+            want = want or bool(G.obb_obb(xf, yf, c, s_, np.float32(hl), np.float32(hw), float(np.float32(so.x)), float(np.float32(so.y)), oc, os_,
+                                          np.float32(hl), np.float32(hw)))
+        assert dc.update(pose, others) == want, k
+        n_hit += edge or inside; n_out += ob.update(pose); n_dyn += want
+    assert n_hit >= 3 and n_out >= 2 and n_dyn >= 3
+    assert sc.update(car(-12.0, -3.0, 0.3).get_pose()) and sc.hit_object == 0
+    assert OutBound().update(car(0, 0, 0).get_pose()) is False               # no boundary: never out (out_bound.py:46-47)
+    ego = car(5.0, 2.0, 0.4)
+    ar = Arrival((5.05, 2.0, 0.4, ego.length / 2, ego.width / 2), threshold=0.95)
+    done, iou = ar.update(ego.get_pose())
+    assert done and abs(iou - G.rect_iou(5.0, 2.0, float(np.float32(0.4)), ego.length / 2, ego.width / 2, 5.05, 2.0, float(np.float32(0.4)), ego.length / 2,
+                                         ego.width / 2)) < 1e-5
+    done, _ = Arrival((9.0, 2.0, 0.4, ego.length / 2, ego.width / 2)).update(ego.get_pose())
+    assert not done
+
+
 def test_batched_env_contract(cuda_device):
     import torch
 

@@ -141,3 +141,40 @@ def test_map_table_one_tile_per_scenario(cuda_device):
         assert np.array_equal(w1.lidar_scan(72, 30.0).cpu().numpy()[0], scan[s])
         w1.close()
     w.close()
+
+
+def test_log_seeded_reset_from_a_levelx_pool(cuda_device, tmp_path):
+    """Log-seeded resets: the pool ``initial_state_pool`` cuts out of a LevelX-schema log goes straight into
+    ``t2d_reset``; the scenarios then tick from the logged states (empty slots stay empty)."""
+    import torch
+
+    from tactics2d_b200 import BatchedWorld
+    from tactics2d_b200.dataset_parser import LevelXParser, initial_state_pool
+    from tests.test_levelx_parser import _write_ind
+
+    _write_ind(tmp_path)
+    parser = LevelXParser("inD")
+    pool, tid, table = initial_state_pool(parser, 3, str(tmp_path), 4, [0, 200, 360])
+    n, m = 6, 4
+    w = BatchedWorld(n, m, table, device=cuda_device, max_step=10)
+    idx = np.array([0, 1, 2, 2, 1, 0], np.int32)
+    w.type_id.copy_(torch.from_numpy(tid[idx]))
+    dev_pool = {k: torch.from_numpy(v).to(cuda_device) for k, v in pool.items()}
+    w.reset(torch.ones(n, dtype=torch.uint8, device=cuda_device), dev_pool, torch.from_numpy(idx).to(cuda_device))
+    torch.cuda.synchronize()
+    got = w.state_numpy()
+    for k in ("x", "y", "heading", "speed", "vx", "vy"):
+        assert np.array_equal(got[k], pool[k][idx]), k
+    before = w.state_numpy()
+    table_o = table.as_oracle_table()
+    act = np.zeros((n, m, 2), np.float32)
+    ref = O.physics_tick(before, tid[idx], act, table_o, 100, 5)
+    w.step(torch.from_numpy(act).to(cuda_device))
+    torch.cuda.synchronize()
+    got = w.state_numpy()
+    active = tid[idx] != 255
+    assert active.sum() == 2 * (2 + 4 + 3)
+    for k in ("x", "y", "speed"):
+        assert np.max(np.abs(got[k] - ref[k])[active] / np.maximum(np.abs(ref[k][active]), 1.0)) <= 1e-5
+    assert np.array_equal(got["x"][~active], before["x"][~active])
+    w.close()
