@@ -513,55 +513,99 @@ struct OneIO {
   float w0, w1;              // SingleTrackDrift only: front / rear wheel angular speed in / out
 };
 
-T2D_HD void dynamics_step(OneIO& io, const Params& p, int n_steps, double dt) {
-  const double lf = p.lf, lr = p.lr, L = (double)p.lf + (double)p.lr;
-  const double accel = clampd(io.a0, p.accel_lo, p.accel_hi);   // :245
-  const double delta = clampd(io.a1, p.steer_lo, p.steer_hi);   // :246
-  io.a0 = (float)accel;
-  io.a1 = (float)delta;
-  const double mass = p.mass, h = p.mass_height, mu = p.mu, Iz = p.I_z, cf = p.cf, cr = p.cr;
-  const double factor_f = (G_ACC * lr - accel * h) / L;          // :145
-  const double factor_r = (G_ACC * lf + accel * h) / L;          // :146
-  const double lf_cf_f = lf * cf * factor_f, lr_cr_r = lr * cr * factor_r;      // :149-150
-  const double lf2_cf_f = lf * lf * cf * factor_f, lr2_cr_r = lr * lr * cr * factor_r;
-  const double cf_f = cf * factor_f, cr_r = cr * factor_r;
-  const double tan_d = tan(delta);
-  const double cos_d = cos(delta);
-  double x = io.x, y = io.y, phi = io.h, v = io.v;
-  double d_phi = v / L * tan_d;                                  // :159
-  double beta = atan(lr / lf * tan_d);                           // :160 (lr/lf, not lr/L)
-  const double vlo = p.speed_lo, vhi = p.speed_hi;
-  const double d_beta_slow = lr / ((1.0 + tan_d * lr / L) * (1.0 + tan_d * lr / L)) / L / (cos_d * cos_d) * delta;  // :194-200
-  for (int it = 0; it < n_steps; ++it) {                          // :163-218
-    double sn, cs;
-    sincos(phi + beta, &sn, &cs);
-    const double dx = v * cs, dy = v * sn;
-    const double v_safe = fabs(v) > 1e-6 ? v : (v >= 0.0 ? 1e-6 : -1e-6);  // :169
-    double d_beta;
-    if (fabs(v) >= 0.1) {                                         // :171
-      const double dd_phi = mu * mass / Iz * (lf_cf_f * delta + (lr_cr_r - lf_cf_f) * beta - (lf2_cf_f + lr2_cr_r) * d_phi / v_safe);
-      d_beta = mu / v_safe * (cf_f * delta - (cr_r + cf_f) * beta + (lr_cr_r - lf_cf_f) * d_phi / v_safe) - d_phi;
-      d_phi += dd_phi * dt;                                       // :192
-    } else {
-      d_beta = d_beta_slow;
-      d_phi += v * cos(beta) / L * tan_d * dt;                    // :210
-    }
-    x += dx * dt;                                                 // :212-216
-    y += dy * dt;
-    v += accel * dt;
-    phi += d_phi * dt;
-    beta += d_beta * dt;
-    v = clampd(v, vlo, vhi);                                      // :218
+// Written over W participants side by side; the kernels use W = 1 (two at a time was measured on B200: the call's
+// register footprint cost more than the second fp64 chain gained - C3 58.7 -> 69.1 us).
+template <int W>
+T2D_HD void dynamics_step_n(OneIO* const (&io)[W], const Params* const (&pp)[W], int n_steps, double dt) {
+  double x[W], y[W], phi[W], v[W], d_phi[W], beta[W], sn[W], cs[W];
+  double accel[W], delta[W], tan_d[W], L[W], vlo[W], vhi[W], d_beta_slow[W], mu[W];
+  double k_a[W], k_sum[W], k_dif[W], k_cc[W], lf_cf_f[W], cf_f[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const Params& p = *pp[i];
+    const double lf = p.lf, lr = p.lr;
+    L[i] = (double)p.lf + (double)p.lr;
+    accel[i] = clampd(io[i]->a0, p.accel_lo, p.accel_hi);   // :245
+    delta[i] = clampd(io[i]->a1, p.steer_lo, p.steer_hi);   // :246
+    io[i]->a0 = (float)accel[i];
+    io[i]->a1 = (float)delta[i];
+    const double mass = p.mass, h = p.mass_height, Iz = p.I_z, cf = p.cf, cr = p.cr;
+    mu[i] = p.mu;
+    const double factor_f = (G_ACC * lr - accel[i] * h) / L[i];          // :145
+    const double factor_r = (G_ACC * lf + accel[i] * h) / L[i];          // :146
+    lf_cf_f[i] = lf * cf * factor_f;                                     // :149-150
+    const double lr_cr_r = lr * cr * factor_r;
+    const double lf2_cf_f = lf * lf * cf * factor_f, lr2_cr_r = lr * lr * cr * factor_r;
+    cf_f[i] = cf * factor_f;
+    const double cr_r = cr * factor_r;
+    tan_d[i] = tan(delta[i]);
+    const double cos_d = cos(delta[i]);
+    x[i] = io[i]->x; y[i] = io[i]->y; phi[i] = io[i]->h; v[i] = io[i]->v;
+    d_phi[i] = v[i] / L[i] * tan_d[i];                                    // :159
+    beta[i] = atan(lr / lf * tan_d[i]);                                   // :160 (lr/lf, not lr/L)
+    vlo[i] = p.speed_lo; vhi[i] = p.speed_hi;
+    d_beta_slow[i] = lr / ((1.0 + tan_d[i] * lr / L[i]) * (1.0 + tan_d[i] * lr / L[i])) / L[i] / (cos_d * cos_d) * delta[i];  // :194-200
+    k_a[i] = mu[i] * mass / Iz; k_sum[i] = lf2_cf_f + lr2_cr_r; k_dif[i] = lr_cr_r - lf_cf_f[i]; k_cc[i] = cr_r + cf_f[i];
+    // (cos, sin)(phi + beta) is carried from sub-step to sub-step by a rotation through the sub-step's change of phi + beta
+    // (a degree-9/10 Taylor pair, exact to 1e-18 for |d| <= 0.1) instead of a double-precision sincos per sub-step; a larger
+    // change (only in the unstable low-speed band) re-evaluates it.  One division per sub-step serves the three quotients
+    // by v_safe.  Both differ from the reference's evaluation order in the last bit only - immaterial outside the band that
+    // is ill-conditioned for ANY float64 implementation (tests/test_oracle_c.py).
+    sincos(phi[i] + beta[i], &sn[i], &cs[i]);
   }
-  double hd = fmod(phi, TWO_PI_D);                               // np.mod(phi, 2 pi) :224
-  if (hd < 0.0) hd += TWO_PI_D;
-  float hn = (float)hd;
-  if (hn >= TWO_PI_HI) hn = 0.0f;
-  float sh, ch;
-  sincos_fast(hn, &sh, &ch);
-  io.x = (float)x; io.y = (float)y; io.h = hn; io.v = (float)v;
-  io.vx = io.v * ch; io.vy = io.v * sh;      // State.velocity of a State without vx, vy (state.py:160-165)
-  io.ch = ch; io.sh = sh;
+  for (int it = 0; it < n_steps; ++it) {                          // :163-218
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const double dx = v[i] * cs[i], dy = v[i] * sn[i];
+      const double v_safe = fabs(v[i]) > 1e-6 ? v[i] : (v[i] >= 0.0 ? 1e-6 : -1e-6);  // :169
+      double d_beta;
+      if (fabs(v[i]) >= 0.1) {                                    // :171
+        const double inv_v = 1.0 / v_safe;
+        const double w = d_phi[i] * inv_v;
+        const double dd_phi = k_a[i] * (lf_cf_f[i] * delta[i] + k_dif[i] * beta[i] - k_sum[i] * w);
+        d_beta = mu[i] * inv_v * (cf_f[i] * delta[i] - k_cc[i] * beta[i] + k_dif[i] * w) - d_phi[i];
+        d_phi[i] += dd_phi * dt;                                  // :192
+      } else {
+        d_beta = d_beta_slow[i];
+        d_phi[i] += v[i] * cos(beta[i]) / L[i] * tan_d[i] * dt;   // :210
+      }
+      x[i] += dx * dt;                                            // :212-216
+      y[i] += dy * dt;
+      v[i] += accel[i] * dt;
+      const double dphi_step = d_phi[i] * dt, dbeta_step = d_beta * dt;
+      phi[i] += dphi_step;
+      beta[i] += dbeta_step;
+      v[i] = clampd(v[i], vlo[i], vhi[i]);                        // :218
+      const double d = dphi_step + dbeta_step;
+      if (fabs(d) <= 0.1) {
+        const double dd = d * d;
+        const double sd = d * (1.0 + dd * (-1.0 / 6 + dd * (1.0 / 120 + dd * (-1.0 / 5040 + dd * (1.0 / 362880)))));
+        const double hd_ = dd * (-0.5 + dd * (1.0 / 24 + dd * (-1.0 / 720 + dd * (1.0 / 40320 + dd * (-1.0 / 3628800)))));   // cos d - 1
+        const double c2 = cs[i] + (cs[i] * hd_ - sn[i] * sd), s2 = sn[i] + (sn[i] * hd_ + cs[i] * sd);
+        cs[i] = c2; sn[i] = s2;
+      } else {
+        sincos(phi[i] + beta[i], &sn[i], &cs[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    double hd = fmod(phi[i], TWO_PI_D);                          // np.mod(phi, 2 pi) :224
+    if (hd < 0.0) hd += TWO_PI_D;
+    float hn = (float)hd;
+    if (hn >= TWO_PI_HI) hn = 0.0f;
+    float sh, ch;
+    sincos_fast(hn, &sh, &ch);
+    io[i]->x = (float)x[i]; io[i]->y = (float)y[i]; io[i]->h = hn; io[i]->v = (float)v[i];
+    io[i]->vx = io[i]->v * ch; io[i]->vy = io[i]->v * sh;      // State.velocity of a State without vx, vy (state.py:160-165)
+    io[i]->ch = ch; io[i]->sh = sh;
+  }
+}
+
+T2D_HD void dynamics_step(OneIO& io, const Params& p, int n_steps, double dt) {
+  OneIO* const ios[1] = {&io};
+  const Params* const ps[1] = {&p};
+  dynamics_step_n<1>(ios, ps, n_steps, dt);
 }
 
 // ------------------------------------------------------------------------------------------
