@@ -50,6 +50,31 @@ BYTES_PER_PARTICIPANT = 16 + 8 + 1 + 24 + 1 + 2 + 2
 BYTES_PER_SCENARIO = 8 + 1 + 1
 
 
+def usable_cores() -> int:
+    """Host cores this process may really use: the scheduler affinity mask, capped by the cgroup CPU quota (a container that
+    reports 128 CPUs may be allowed 8 of them - a worker pool sized by os.cpu_count() then only thrashes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota = None
+        if os.path.exists("/sys/fs/cgroup/cpu.max"):
+            q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+        elif os.path.exists("/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        if quota is not None:
+            n = max(1, min(n, int(quota + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -195,15 +220,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     scene = make_scene(args.config, seed=1, n=args.scenarios or None)
     n, m = scene.shape
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bounded: the whole run must end within a few minutes - ~2 k participant-steps/s per core measured for the port
     est = n * m / (1900.0 * max(1, cores)) * (steps + warmup)
-    if est > 240.0:
+    if est > 150.0:
         warmup = min(warmup, 1)
-        steps = max(1, min(steps, int(240.0 / max(1e-9, n * m / (1900.0 * cores))) - warmup))
+        steps = max(1, min(steps, int(150.0 / max(1e-9, n * m / (1900.0 * cores))) - warmup))
     value, t_step = cpu_port_throughput(scene, n, cores, steps=steps, warmup=warmup, per_job=32)
     sample = (f"the whole batch every step: {n} scenarios x {m} participants, {steps} timed steps after {warmup} warm-up, "
               f"{cores} worker processes x jobs of 32 scenarios (per-agent Python loop = the reference's execution model; "
@@ -533,7 +558,7 @@ def run_ours(args):
                          "note": "achieved = algorithmic bytes per launch / mean launch duration inside the timed CUDA-graph region"},
         }
         if world_size == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             n_s = 16
             v1, _ = cpu_port_throughput(scene0, n_s, 1)
             line["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",

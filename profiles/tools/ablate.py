@@ -11,7 +11,8 @@ n, m, K, R = int(os.environ.get("ABL_N", 4096)), int(os.environ.get("ABL_M", 64)
 
 
 def run(name, interval=100, use_map=True, use_bounds=True, physics=True, shapeless=False):
-    worlds, acts = [], []
+    worlds, acts, pools = [], [], []
+    ones = torch.ones(n, dtype=torch.uint8, device=dev)
     for r in range(R):
         sc = synthetic.config2(n, m, seed=1 + r)
         table = sc.table
@@ -23,6 +24,7 @@ def run(name, interval=100, use_map=True, use_bounds=True, physics=True, shapele
         w.set_state(sc.x, sc.y, sc.heading, sc.speed, type_id=sc.type_id)
         worlds.append(w)
         acts.append(torch.from_numpy(synthetic.random_actions(9000 + r, (n, m))).to(dev))
+        pools.append({k: getattr(w, k).clone() for k in ("x", "y", "heading", "speed", "vx", "vy")})
 
     def body():
         for i in range(K):
@@ -43,6 +45,9 @@ def run(name, interval=100, use_map=True, use_bounds=True, physics=True, shapele
     torch.cuda.synchronize()
     ts = []
     for _ in range(15):
+        for w, p in zip(worlds, pools):   # fresh states every repetition, as bench.py does
+            w.reset(ones, p)
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) / K * 1e3)
