@@ -178,3 +178,81 @@ def test_log_seeded_reset_from_a_levelx_pool(cuda_device, tmp_path):
         assert np.max(np.abs(got[k] - ref[k])[active] / np.maximum(np.abs(ref[k][active]), 1.0)) <= 1e-5
     assert np.array_equal(got["x"][~active], before["x"][~active])
     w.close()
+
+
+def test_worlds_of_different_size_interleave(cuda_device):
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per kernel and process-wide; a small world configured
+    after a big one must not lower the big one's opt-in (tracked per device and kernel variant, only ever raised)."""
+    import torch
+
+    from tactics2d_b200 import BatchedWorld, synthetic
+    from tactics2d_b200.map import load_collidable_segments
+
+    seg, bounds = load_collidable_segments("rounD_0")       # a large tile: tens of KB of shared memory per CTA
+    big = synthetic.config5(4096, 128, seed=51, segments=seg, bounds=bounds)       # 8 warps per CTA, big map
+    small = synthetic.config2(8, 16, seed=52, size=40.0)                           # 2 warps per CTA, tiny map
+    wb = BatchedWorld(*big.shape, big.table, device=cuda_device)
+    wb.set_map(big.segments, big.bounds)
+    wb.set_state(big.x, big.y, big.heading, big.speed, type_id=big.type_id)
+    ws = BatchedWorld(*small.shape, small.table, device=cuda_device)
+    ws.set_map(small.segments, small.bounds)
+    ws.set_state(small.x, small.y, small.heading, small.speed, type_id=small.type_id)
+    ab = torch.zeros((*big.shape, 2), device=cuda_device)
+    as_ = torch.zeros((*small.shape, 2), device=cuda_device)
+    table_b, table_s = big.table.as_oracle_table(), small.table.as_oracle_table()
+    for _ in range(2):
+        for w, a, sc, tb in ((wb, ab, big, table_b), (ws, as_, small, table_s), (wb, ab, big, table_b)):
+            r = w.step(a)
+            torch.cuda.synchronize()
+            got = w.state_numpy()
+            sel = slice(0, 8)
+            fl, hi, hs = O.events(got["x"][sel], got["y"][sel], got["heading"][sel], sc.type_id[sel], tb, sc.segments, sc.bounds)
+            assert np.array_equal(r.flags.cpu().numpy()[sel], fl) and np.array_equal(r.hit_segment.cpu().numpy()[sel], hs)
+    wb.close(); ws.close()
+
+
+def test_masked_reset_starts_wheel_speeds_and_last_accel_fresh(cuda_device):
+    """a masked reset re-initialises ALL per-participant state the world owns: the SingleTrackDrift wheel speeds
+    (pool columns, or free rolling speed / wheel_radius) and the controllers' State.accel of the previous tick (0)."""
+    import torch
+
+    from tactics2d_b200 import BatchedWorld, TypeParams, TypeTable
+    from tactics2d_b200.controller import AccelerationController
+
+    n, m = 6, 8
+    table = TypeTable([TypeParams.vehicle("medium_car", model="drift")])
+    w = BatchedWorld(n, m, table, device=cuda_device)
+    z = np.zeros((n, m), np.float32)
+    speed = np.full((n, m), 6.0, np.float32)
+    w.set_state(z, z, z, speed, type_id=np.zeros((n, m), np.uint8))
+    w.set_wheel_state(speed / 0.344, speed / 0.344)
+    cid = np.zeros((n, m), np.uint8)
+    w.set_controllers([AccelerationController(12.0)], cid)
+    act = torch.zeros((n, m, 2), device=cuda_device)
+    for _ in range(3):
+        w.control(act); w.step(act)
+    torch.cuda.synchronize()
+    assert float(w.last_accel.abs().max()) > 0 and not torch.allclose(w.omega_front, torch.from_numpy(speed / 0.344).to(cuda_device))
+    mask = torch.tensor([1, 0, 1, 0, 0, 1], dtype=torch.uint8, device=cuda_device)
+    pool = {k: torch.from_numpy(v).to(cuda_device) for k, v in dict(x=z, y=z, heading=z, speed=np.full((n, m), 4.0, np.float32)).items()}
+    before = (w.omega_front.clone(), w.omega_rear.clone(), w.last_accel.clone())
+    w.reset(mask, pool)
+    torch.cuda.synchronize()
+    mb = mask.bool()
+    wr = float(np.float32(4.0) / np.float32(table.rows[0].wheel_radius))
+    assert torch.allclose(w.omega_front[mb], torch.full_like(w.omega_front[mb], wr)) and torch.allclose(w.omega_rear[mb], torch.full_like(w.omega_rear[mb], wr))
+    assert float(w.last_accel[mb].abs().max()) == 0.0
+    assert torch.equal(w.omega_front[~mb], before[0][~mb]) and torch.equal(w.last_accel[~mb], before[2][~mb])     # untouched scenarios
+    pool["omega_wf"] = torch.full((n, m), 9.0, device=cuda_device)
+    pool["omega_wr"] = torch.full((n, m), 8.0, device=cuda_device)
+    w.reset(mask, pool)
+    torch.cuda.synchronize()
+    assert float(w.omega_front[mb].min()) == 9.0 and float(w.omega_rear[mb].max()) == 8.0
+    # arguments that would be raw-pointer accidents are rejected on the host
+    with pytest.raises(ValueError):
+        w.reset(torch.ones(n + 1, dtype=torch.uint8, device=cuda_device), pool)
+    with pytest.raises(ValueError):
+        w.reset(mask, {**pool, "x": pool["x"].cpu()})
+    w.reset(mask.cpu(), pool)          # a host mask is moved, not dereferenced on the device
+    torch.cuda.synchronize()
+    w.close()
