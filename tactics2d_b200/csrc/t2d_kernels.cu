@@ -294,6 +294,15 @@ __device__ __noinline__ void pair_resolve(int ti, int tj, int mp_shift, int psh,
   }
 }
 
+// Packed fp32 pair operations of the partner loop (T2D_SCALAR_PAIR: measurement builds fall back to two scalar operations).
+#if defined(T2D_SCALAR_PAIR)
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+
 // One word of the partner loop = IPW iterations x PPL own participants x 2 partners.  X / Y: the partner positions of
 // the word's iterations (two per float2); nx2 / ny2: the lane's own positions, negated; nthr2: minus the squared
 // broadphase reach.  The margin of a pair, d^2 - thr, is <= 0 for a candidate; a NaN position (empty slot) gives a NaN
@@ -309,8 +318,8 @@ __device__ __forceinline__ float pair_word_min(const float2 (&X)[16 / PPL], cons
     for (int i = 0; i < PPL; ++i) {
       const bool v0 = !FIRST || (2 * uu - i >= 1), v1 = !FIRST || (2 * uu + 1 - i >= 1);
       if (!v0 && !v1) continue;
-      const float2 dx = __fadd2_rn(X[uu], nx2[i]), dy = __fadd2_rn(Y[uu], ny2[i]);
-      const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2[i]));
+      const float2 dx = pk_add(X[uu], nx2[i]), dy = pk_add(Y[uu], ny2[i]);
+      const float2 d2 = pk_fma(dx, dx, pk_fma(dy, dy, nthr2[i]));
       if (v0 && v1) m = fminf(m, fminf(d2.x, d2.y));
       else if (v0) m = fminf(m, d2.x);
       else m = fminf(m, d2.y);
@@ -330,8 +339,8 @@ __device__ __forceinline__ unsigned pair_word_bits(const float2 (&X)[16 / PPL], 
     for (int i = 0; i < PPL; ++i) {
       const bool v0 = !FIRST || (2 * uu - i >= 1), v1 = !FIRST || (2 * uu + 1 - i >= 1);
       if (!v0 && !v1) continue;
-      const float2 dx = __fadd2_rn(X[uu], nx2[i]), dy = __fadd2_rn(Y[uu], ny2[i]);
-      const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2[i]));
+      const float2 dx = pk_add(X[uu], nx2[i]), dy = pk_add(Y[uu], ny2[i]);
+      const float2 d2 = pk_fma(dx, dx, pk_fma(dy, dy, nthr2[i]));
       if (v0 && d2.x <= 0.0f) bits |= 1u << ((uu * PPL + i) * 2);
       if (v1 && d2.y <= 0.0f) bits |= 2u << ((uu * PPL + i) * 2);
     }

@@ -36,6 +36,14 @@
 #define T2D_RSQRTF(x) (1.0f / sqrtf(x))
 #endif
 
+#define T2D_PRAGMA_(x) _Pragma(#x)
+#define T2D_PRAGMA(x) T2D_PRAGMA_(x)
+#if defined(T2D_KIN_UNROLL)   // measurement builds: unroll factor of the kinematic sub-step loop
+#define T2D_KIN_UNROLL_PRAGMA T2D_PRAGMA(unroll T2D_KIN_UNROLL)
+#else
+#define T2D_KIN_UNROLL_PRAGMA
+#endif
+
 namespace t2d {
 
 constexpr int MODEL_KINEMATICS = 0;
@@ -340,7 +348,10 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
     float v[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) v[i] = io.v[i];
-#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    // (The packed FFMA2 form of this loop - two participants per instruction, the same operations - is kept for measurement
+    //  builds, -DT2D_PACKED_KIN_LOOP: on B200 it is no faster than four scalar chains, 13.9 vs 13.7 us per tick at 4096 x 64:
+    //  FFMA2 occupies the FMA pipe for two cycles, and four independent scalar chains hide their latency better than two packed ones.)
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && defined(T2D_PACKED_KIN_LOOP)
     if constexpr (W == 4) {
       float2 C2[2], S2[2], V2[2], SX2[2], SY2[2], H2[2], NSN2[2], SE2[2], NSE2[2], HE2[2], ADT2[2], W12[2];
 #pragma unroll
@@ -385,6 +396,7 @@ T2D_HD void kinematics_step(KinIO<W>& io, const Params* const (&p)[W], int n_ste
 #endif
     {
       float fi = -1.0f;
+      T2D_KIN_UNROLL_PRAGMA
       for (int it = 0; it < n_steps; ++it) {
         fi += 1.0f;
 #pragma unroll
