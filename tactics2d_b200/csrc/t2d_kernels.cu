@@ -602,6 +602,20 @@ __device__ __noinline__ unsigned ego_goal_events(const StepArgs& A, long long n,
   return r;
 }
 
+// L2 prefetch of the lines a lane's PPL participants will load (state, action, type ids).
+__device__ __forceinline__ void prefetch_tile_l2(const StepArgs& A, long long i) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + i));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + i));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.h + i));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.v + i));
+  if (A.action) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.action + 2 * i));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.type_id + i));
+  if (A.needs_vel_in) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vx + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vy + i));
+  }
+}
+
 // ---------------------------------------------------------------------------- K1
 // KIN_ONLY: every type in the table is SingleTrackKinematics or static - the fp64 models are compiled out
 // (their register footprint would otherwise bound the occupancy of the whole kernel).
@@ -654,6 +668,15 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     if (map_smem_bytes > 0) bulk_g2s(s_map, A.map_blob, (uint32_t)map_smem_bytes, s_bar);
   }
   bool staged = false;
+  // L2 prefetch of the first tile's state / action lines while the previous grid drains (its CTAs retire over a
+  // microsecond or two; ours take their places one by one and would otherwise just sit in griddepcontrol.wait): L2 is the
+  // coherence point of the GPU, so a line fetched early can never be stale when it is loaded after the wait.  Measured
+  // at 4096 x 64 with cold inputs: 13.7 -> 12.9 us per tick.
+  {
+    const long long n_ = ((long long)blockIdx.x * wpc + warp) * (32 >> A.g_shift) + (lane >> A.g_shift);
+    const int m_ = (lane & (A.G - 1)) * PPL;
+    if (n_ < A.N && m_ < A.M) prefetch_tile_l2(A, n_ * A.M + m_);   // (inside the arrays: a hint, but no stray addresses)
+  }
   // ... and wait here, before the first access to the state the previous tick wrote, until that grid has
   // completed and flushed (no-op when the kernel was not launched as a programmatic dependent).
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -747,6 +770,10 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
           }
         }
       }
+    }
+    {   // several tiles per warp (persistent CTAs): the next tile's lines start their way to L2 now
+      const long long n_next = n + (long long)gridDim.x * wpc * spw;
+      if (n_next < A.N && m0 < M) prefetch_tile_l2(A, n_next * M + m0);
     }
     if (A.ego_action != nullptr && A.do_physics && gl == 0 && scn_ok) {   // the ego's action comes from its own [N, 2] array
       const float2 ea = reinterpret_cast<const float2*>(A.ego_action)[n];
