@@ -94,6 +94,7 @@ struct StepArgs {
   double dt_d, dt_rem_d, interval_d;   // the same steps in double (dynamics / point mass run in fp64)
   int max_step, cfg_flags;
   int do_physics, has_bounds, vec_ok, needs_vel_in;
+  int prefetch;                    // L2 prefetch of tile inputs ahead of their loads (see the kernel prologue)
   float bxmin, bxmax, bymin, bymax;
   float rb_max;                    // largest bounding radius in the type table (broadphase threshold)
   const float* goal_target;        // [N][5] cx, cy, heading, half_len, half_wid of the target area, or nullptr
@@ -671,11 +672,14 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
   // L2 prefetch of the first tile's state / action lines while the previous grid drains (its CTAs retire over a
   // microsecond or two; ours take their places one by one and would otherwise just sit in griddepcontrol.wait): L2 is the
   // coherence point of the GPU, so a line fetched early can never be stale when it is loaded after the wait.  Measured
-  // at 4096 x 64 with cold inputs: 13.7 -> 12.9 us per tick.
+  // at 4096 x 64 with cold inputs: 13.7 -> 12.65 us per tick on one GPU.  With a peer-memory done exchange running under
+  // the tick (8 GPUs) the same build measured SLOWER than without the prefetch (16.9 vs 14.25 us per step: the burst of
+  // prefetches competes with the exchange kernel's peer stores and system-scope fence, and the exchange chain then sets
+  // the pace), so the host leaves it off while an exchange object is alive in the process (T2D_PREFETCH=0 / 1 overrides).
   {
     const long long n_ = ((long long)blockIdx.x * wpc + warp) * (32 >> A.g_shift) + (lane >> A.g_shift);
     const int m_ = (lane & (A.G - 1)) * PPL;
-    if (n_ < A.N && m_ < A.M) prefetch_tile_l2(A, n_ * A.M + m_);   // (inside the arrays: a hint, but no stray addresses)
+    if (A.prefetch && n_ < A.N && m_ < A.M) prefetch_tile_l2(A, n_ * A.M + m_);   // (inside the arrays: a hint, but no stray addresses)
   }
   // ... and wait here, before the first access to the state the previous tick wrote, until that grid has
   // completed and flushed (no-op when the kernel was not launched as a programmatic dependent).
@@ -773,7 +777,7 @@ __global__ void T2D_K1_BOUNDS t2d_step_kernel(const __grid_constant__ StepArgs A
     }
     {   // several tiles per warp (persistent CTAs): the next tile's lines start their way to L2 now
       const long long n_next = n + (long long)gridDim.x * wpc * spw;
-      if (n_next < A.N && m0 < M) prefetch_tile_l2(A, n_next * M + m0);
+      if (A.prefetch && n_next < A.N && m0 < M) prefetch_tile_l2(A, n_next * M + m0);
     }
     if (A.ego_action != nullptr && A.do_physics && gl == 0 && scn_ok) {   // the ego's action comes from its own [N, 2] array
       const float2 ea = reinterpret_cast<const float2*>(A.ego_action)[n];
@@ -1722,6 +1726,7 @@ using namespace t2d;
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_exchanges_alive{0};   // peer-memory done exchanges in this process (see StepArgs::prefetch)
 static std::mutex g_smem_mutex;
 static int g_smem_configured[64][4];   // [device][kernel variant]: dynamic shared memory opted in so far (process-wide)
 
@@ -1781,6 +1786,7 @@ struct t2d_ctx {
   float goal_threshold = 0.95f;
   int goal_noact_max = 0;
   bool use_pdl = true;             // T2D_PDL=0 disables programmatic dependent launch
+  int prefetch_override = -1;      // T2D_PREFETCH=0 / 1 (experiments; -1 = on unless a done exchange is alive)
   int wpc_override = 0;            // T2D_WPC=w: warps per CTA of the tick (experiments; 0 = pick from the batch size)
   int grid_limit = 0;              // T2D_GRID_LIMIT=k: at most k CTAs of the persistent tick grid per SM (experiments; 0 = occupancy)
   long long* dbg_clock = nullptr;
@@ -1842,6 +1848,7 @@ int t2d_create(t2d_ctx** out, int device, int n_scenarios, int m_participants, c
   c->ppl = ppl;
   if (const char* e = getenv("T2D_PDL")) c->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("T2D_GRID_LIMIT")) c->grid_limit = std::max(0, atoi(e));
+  if (const char* e = getenv("T2D_PREFETCH")) c->prefetch_override = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("T2D_WPC")) {
     const int v = atoi(e);
     if (v >= 1 && v <= MAX_WARPS_PER_CTA) c->wpc_override = v;
@@ -2263,6 +2270,7 @@ static int launch_step(t2d_ctx* c, const float* action, uint8_t* flags, int16_t*
   A.max_step = c->cfg.max_step; A.cfg_flags = c->cfg.flags;
   A.do_physics = do_physics; A.has_bounds = c->has_bounds ? 1 : 0;
   A.bxmin = c->bounds[0]; A.bxmax = c->bounds[1]; A.bymin = c->bounds[2]; A.bymax = c->bounds[3];
+  A.prefetch = c->prefetch_override >= 0 ? c->prefetch_override : (g_exchanges_alive.load() == 0 ? 1 : 0);
   A.needs_vel_in = (c->has_pointmass || c->has_drift) ? 1 : 0;   // (drift: K1 passes the pre-pass's vx, vy through)
   bool vec = (c->M % c->ppl == 0) && aligned16(A.x) && aligned16(A.y) && aligned16(A.h) && aligned16(A.v) && aligned16(A.vx) &&
              aligned16(A.vy) && (reinterpret_cast<uintptr_t>(A.type_id) % 4 == 0) && (!action || aligned16(action)) &&
@@ -2652,6 +2660,7 @@ int t2d_exchange_create(t2d_exchange** out, int device, int world, int rank, int
   }
   memcpy(ipc_handle_out, &h, sizeof(h));
   CUDA_TRY(cudaDeviceSynchronize());
+  g_exchanges_alive.fetch_add(1);
   *out = x;
   return T2D_OK;
 }
@@ -2712,6 +2721,7 @@ int t2d_exchange_destroy(t2d_exchange* x) {
   for (int p = 0; p < x->world; ++p)
     if (x->connected && p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
   if (x->base) cudaFree(x->base);
+  g_exchanges_alive.fetch_sub(1);
   delete x;
   return T2D_OK;
 }
