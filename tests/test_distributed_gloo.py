@@ -154,3 +154,24 @@ def test_peer_exchange_setup_is_agreed_on_by_all_ranks(mode):
         assert all(r[1] == "raised" and "unavailable" in r[2] for r in results)
         bad = 1 if mode == "connect" else 0
         assert all(f"{bad}:" in r[2] for r in results)
+
+
+def test_peer_exchange_lag_arguments_are_validated_before_any_device_call():
+    """A lag of k steps needs a ring of 2 k + 2 slots; negative lags are rejected (host logic, no GPU)."""
+    import torch.distributed as dist
+
+    from tactics2d_b200.distributed import PeerDoneExchange
+
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1)
+    try:
+        with pytest.raises(ValueError):
+            PeerDoneExchange(64, "cpu", lag=-1, lib=_FakeExchangeLib(0))
+        with pytest.raises(ValueError):
+            PeerDoneExchange(64, "cpu", slots=4, lag=2, lib=_FakeExchangeLib(0))
+        ex = PeerDoneExchange(64, "cpu", lag=2, lib=_FakeExchangeLib(0))
+        assert ex.slots >= 6 and ex.lag == 2 and ex.calls == 0
+    finally:
+        if own:
+            dist.destroy_process_group()

@@ -135,3 +135,66 @@ def test_pose_corner_order_follows_reference_ring():
     """vehicle.py:133-140: [(+L/2,-W/2), (+L/2,+W/2), (-L/2,+W/2), (-L/2,-W/2)] rotated by the heading."""
     cs = G.obb_corners(10.0, 5.0, np.pi / 2, 2.142, 0.8995)
     np.testing.assert_allclose(cs, [[10.8995, 7.142], [9.1005, 7.142], [9.1005, 2.858], [10.8995, 2.858]], atol=1e-12)
+
+
+def _winding_inside(poly, p):
+    """Exact point-in-(possibly concave)-polygon by the winding number over rational coordinates; None on the boundary."""
+    wn = 0
+    n = len(poly)
+    for i in range(n):
+        a, b = poly[i], poly[(i + 1) % n]
+        if orient(a, b, p) == 0 and on_seg(a, b, p):
+            return None
+        if a[1] <= p[1]:
+            if b[1] > p[1] and orient(a, b, p) > 0:
+                wn += 1
+        elif b[1] <= p[1] and orient(a, b, p) < 0:
+            wn -= 1
+    return wn != 0
+
+
+def test_pose_vs_area_polygon_matches_exact_definition():
+    """oracle.scenario.events with poly_start (a pose intersects an Area polygon iff one of its edges meets the pose OR the
+    pose centre lies inside; the first OBJECT hit is reported by its first segment) against the exact-rational statement of
+    shapely's `pose.intersects(polygon)` for closed sets: two boundaries share a point, or one shape contains a point of the
+    other - on convex and concave rings, including poses wholly inside, rings wholly inside the pose, and touching."""
+    from oracle import scenario as O
+    from tactics2d_b200.map import polygons_to_segments
+
+    rings = [
+        [(F(-30), F(18)), (F(30), F(18)), (F(30), F(19)), (F(-30), F(19))],
+        [(F(-25), F(-20)), (F(-5), F(-20)), (F(-5), F(-4)), (F(-25), F(-4))],
+        [(F(4), F(-18)), (F(16), F(-18)), (F(16), F(-6)), (F(12), F(-6)), (F(12), F(-14)), (F(4), F(-14))],    # concave
+        [(F(20), F(5)), (F(41, 2), F(5)), (F(41, 2), F(11, 2)), (F(20), F(11, 2))],                             # smaller than the pose
+    ]
+    seg, ps = polygons_to_segments([[(float(x), float(y)) for x, y in r] for r in rings])
+    table = dict(half_len=np.array([2.0], np.float32), half_wid=np.array([1.0], np.float32), radius=np.array([0.0], np.float32),
+                 shape=np.array([0], np.int32), model=np.array([0], np.int32))
+    for k in O.TABLE_FLOAT_FIELDS:
+        table.setdefault(k, np.array([1.0], np.float32))
+    rng = np.random.default_rng(1)
+    n_inside_only = n_hit = n_free = 0
+    cases = [(F(-15), F(-12), 2), (F(8), F(-10), 0), (F(81, 4), F(21, 4), 3), (F(0), F(37, 2), 1), (F(-3), F(-12), 0)]   # hand-placed
+    for _ in range(400):
+        cases.append((F(int(rng.integers(-140, 141)), 4), F(int(rng.integers(-100, 101)), 4), int(rng.integers(0, len(TRIPLES)))))
+    for x, y, t in cases:
+        c, s = TRIPLES[t]
+        pose = corners(x, y, c, s, F(2), F(1))
+        want = -1
+        for p, ring in enumerate(rings):
+            hit = any(seg_seg(pose[i], pose[(i + 1) % 4], ring[j], ring[(j + 1) % len(ring)]) for i in range(4) for j in range(len(ring)))
+            if not hit:
+                ins = _winding_inside(ring, (x, y))
+                hit = bool(ins) or in_convex(pose, ring[0])          # pose inside the ring / ring inside the pose
+            if hit:
+                want = int(ps[p])
+                break
+        heading = float(np.arctan2(float(s), float(c)))
+        fl, hi, hs = O.events(np.array([[f(x)]]), np.array([[f(y)]]), np.array([[heading]]), np.zeros((1, 1), np.uint8), table, seg, None, poly_start=ps)
+        assert int(hs[0, 0]) == want, (x, y, t, int(hs[0, 0]), want)
+        assert bool(fl[0, 0] & 2) == (want >= 0)
+        plain = O.events(np.array([[f(x)]]), np.array([[f(y)]]), np.array([[heading]]), np.zeros((1, 1), np.uint8), table, seg, None)[2][0, 0]
+        n_inside_only += int(want >= 0 and plain < 0)
+        n_hit += int(want >= 0)
+        n_free += int(want < 0)
+    assert n_inside_only >= 5 and n_hit >= 40 and n_free >= 100, (n_inside_only, n_hit, n_free)
