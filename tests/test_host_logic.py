@@ -230,3 +230,34 @@ def test_osm_parser_rules(tmp_path):
     seg = collidable_segments(m)
     assert seg.shape == (2, 4) and seg[1] == pytest.approx([111.32, 0.0, 111.32, 110.54])
     assert m.boundary == (0.0, 112.0, 0.0, 111.0)
+
+
+def test_polygons_to_segments_and_pose_recovery():
+    """Host helpers of round 2: static objects -> tile format; a get_pose() ring -> (centre, heading, half extents)."""
+    from tactics2d_b200.map import polygons_to_segments
+    from tactics2d_b200.participant.element import Vehicle
+    from tactics2d_b200.participant.trajectory import State
+    from tactics2d_b200.traffic.event_detection.detectors import _pose_to_rect
+
+    seg, ps = polygons_to_segments([[(0, 0), (4, 0), (4, 3), (0, 3), (0, 0)], [(10, 10), (12, 10), (11, 12)]], [[(20, 0), (22, 0), (22, 5)]])
+    assert ps.tolist() == [0, 4, 7] and seg.shape == (9, 4) and seg.dtype == np.float32
+    for p0, p1 in zip(ps[:-1], ps[1:]):                       # rings chain and close
+        ring = seg[p0:p1]
+        assert np.array_equal(ring[:, 2:], np.roll(ring[:, :2], -1, axis=0))
+    assert np.array_equal(seg[7], [20, 0, 22, 0]) and np.array_equal(seg[8], [22, 0, 22, 5])      # the open line keeps its pieces
+    with pytest.raises(ValueError):
+        polygons_to_segments([[(0, 0), (1, 1)]])
+    v = Vehicle(id_=0)
+    v.load_from_template("medium_car")
+    for h in (0.3, 2.9, 4.0, 6.1):
+        v.add_state(State(frame=int(h * 1000), x=12.5, y=-3.25, heading=h, speed=0.0))
+        cx, cy, hh, hl, hw = _pose_to_rect(v.get_pose())
+        assert abs(cx - 12.5) < 1e-12 and abs(cy + 3.25) < 1e-12
+        assert abs(np.angle(np.exp(1j * (hh - h)))) < 1e-12
+        assert abs(hl - v.length / 2) < 1e-12 and abs(hw - v.width / 2) < 1e-12
+
+    class _ShapelyLike:                                       # anything with .exterior.coords (a shapely Polygon) works too
+        class exterior:
+            coords = [tuple(p) for p in v.get_pose()] + [tuple(v.get_pose()[0])]
+
+    assert np.allclose(_pose_to_rect(_ShapelyLike()), _pose_to_rect(v.get_pose()))
