@@ -479,8 +479,10 @@ def run_ours(args):
 
         def ego_step(i):
             r = i % R
-            worlds[r].step_host_ego(host_ego[i % len(host_ego)], npc_act[r])
+            done_np, _ = worlds[r].step_host_ego(host_ego[i % len(host_ego)], npc_act[r])
             if world_size > 1:
+                # t2d_step_host_ego delivers status / done to the HOST; the exchange takes the device copy of this step's mask
+                worlds[r].result.done.copy_(torch.from_numpy(done_np), non_blocking=True)
                 if peer is not None:
                     peer(worlds[r].result.done, done_all)
                 else:
