@@ -488,7 +488,8 @@ def run_ours(args):
                 else:
                     dist.all_gather_into_tensor(done_all, worlds[r].result.done)
         t_ego = timed_loop(ego_step, reps_e2e)
-        e2e = {"value": world_size * n * m / (t_ego * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": 2 * n,
+        e2e = {"value": world_size * n * m / (t_ego * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4 + (n if world_size > 1 else 0),
+               "d2h_bytes_per_step": 2 * n,
                "ms_per_step": t_ego,
                "api": ("BatchedWorld.step_host_ego(ego_action) = t2d_step_host_ego: pinned-host ego actions [N, 2] -> device, on-device "
                        "IDM controllers for the other participants (t2d_control), the fused tick, status + done -> host, stream sync "
