@@ -164,7 +164,7 @@ class BatchedWorld:
         """A different map per scenario: ``tiles`` is a list of dicts ``{"segments": [S, 4], "bounds": (4,) or None,
         "poly_start": [P + 1] or None}`` (what ``_ParkingScenarioManager.reset`` builds per episode - the lot's wall and
         obstacle Areas and ``map_.boundary``, envs/parking.py:397-441 - or the reference's ``data/*_map`` files, one tile
-        each), ``tile_id`` an integer array [N]: the tile of every scenario.  The ids live in ``self.tile_id`` (uint16
+        each: ``map.polygons_to_segments(map.load_areas(name, subtypes), [lines])``), ``tile_id`` an integer array [N]: the tile of every scenario.  The ids live in ``self.tile_id`` (uint16
         device tensor) and may be rewritten between ticks."""
         keep, rows = [], (_lib.MapTileC * len(tiles))()
         for i, t in enumerate(tiles):

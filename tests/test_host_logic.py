@@ -232,6 +232,149 @@ def test_osm_parser_rules(tmp_path):
     assert m.boundary == (0.0, 112.0, 0.0, 111.0)
 
 
+def test_osm_area_relations_chain_into_rings(tmp_path):
+    """``_load_area_lanelet2`` (parse_osm.py:461-510): outer ways are chained end to end whichever way round they were drawn
+    (:48-60), inner ways start a new hole whenever the current one closes, deleted relations are skipped, ways that do not
+    touch raise SyntaxError."""
+    from tactics2d_b200.map import Area, parse_osm_lanelet2, polygons_to_segments
+
+    def nodes(pts):
+        return "".join(f"<node id='{i + 1}' lat='{la}' lon='{lo}'/>" for i, (la, lo) in enumerate(pts))
+
+    def way(id_, refs):
+        return f"<way id='{id_}'>" + "".join(f"<nd ref='{r}'/>" for r in refs) + "<tag k='type' v='virtual'/></way>"
+
+    # outer square 1-2-3-4 drawn as four ways in mixed directions; holes 5-6-7 (one way, closed) and 8-9-10 (two ways)
+    pts = [(0, 0), (0, 0.001), (0.001, 0.001), (0.001, 0), (0.0002, 0.0002), (0.0002, 0.0004), (0.0004, 0.0003),
+           (0.0006, 0.0006), (0.0006, 0.0008), (0.0008, 0.0007), (0.01, 0.01), (0.01, 0.011)]
+    body = nodes(pts) + way(20, [1, 2]) + way(21, [3, 2]) + way(22, [3, 4]) + way(23, [1, 4]) + way(24, [5, 6, 7, 5]) \
+        + way(25, [8, 9]) + way(26, [8, 10, 9]) + way(27, [11, 12])
+    rel = ("<relation id='30'><member type='way' ref='20' role='outer'/><member type='way' ref='21' role='outer'/>"
+           "<member type='way' ref='22' role='outer'/><member type='way' ref='23' role='outer'/>"
+           "<member type='way' ref='24' role='inner'/><member type='way' ref='25' role='inner'/><member type='way' ref='26' role='inner'/>"
+           "<member type='relation' ref='99' role='regulatory_element'/>"
+           "<tag k='type' v='multipolygon'/><tag k='subtype' v='vegetation'/></relation>"
+           "<relation id='31' action='delete'><member type='way' ref='20' role='outer'/><tag k='type' v='multipolygon'/></relation>"
+           "<relation id='32'><member type='way' ref='20' role='left'/><member type='way' ref='22' role='right'/><tag k='type' v='lanelet'/></relation>")
+    osm = tmp_path / "a.osm"
+    osm.write_text("<?xml version='1.0'?><osm>" + body + rel + "</osm>")
+    m = parse_osm_lanelet2(str(osm))
+    assert [a.id_ for a in m.areas] == [30]
+    a = m.areas[0]
+    assert (a.type_, a.subtype, a.closed) == ("multipolygon", "vegetation", True)
+    assert a.outer.shape == (4, 2) and [h.shape for h in a.inners] == [(3, 2), (3, 2)]
+    corner = {tuple(np.round(p, 6)) for p in a.outer}
+    assert corner == {(0.0, 0.0), (111.32, 0.0), (111.32, 110.54), (0.0, 110.54)}
+    d = np.abs(np.roll(a.outer, -1, 0) - a.outer)
+    assert ((d[:, 0] < 1e-9) ^ (d[:, 1] < 1e-9)).all()                              # consecutive vertices share a side
+    seg, ps = polygons_to_segments(m.areas, [w.points for w in m.ways if w.id_ == 27])
+    assert ps.tolist() == [0, 10] and len(seg) == 11
+    for r0, r1 in ((0, 4), (4, 7), (7, 10)):                                        # every ring closes on itself
+        assert np.array_equal(seg[r0:r1, 2:], np.roll(seg[r0:r1, :2], -1, axis=0))
+
+    broken = tmp_path / "b.osm"
+    broken.write_text("<?xml version='1.0'?><osm>" + body + "<relation id='40'><member type='way' ref='20' role='outer'/>"
+                      "<member type='way' ref='27' role='outer'/><tag k='type' v='multipolygon'/></relation></osm>")
+    with pytest.raises(SyntaxError):
+        parse_osm_lanelet2(str(broken))
+    open_ = tmp_path / "c.osm"
+    open_.write_text("<?xml version='1.0'?><osm>" + body + "<relation id='41'><member type='way' ref='20' role='outer'/>"
+                     "<member type='way' ref='21' role='outer'/><tag k='type' v='multipolygon'/></relation></osm>")
+    assert parse_osm_lanelet2(str(open_)).areas[0].closed is False                  # the reference only warns (:491-492)
+
+
+def test_packaged_maps_carry_their_areas():
+    """The 96 Lanelet2 areas of the reference's inD / rounD maps (``data/{inD,rounD}_map/*.osm``; the highD maps have none),
+    compiled into the packaged tiles: every exterior chains closed, the counts per subtype are the files', the one area with
+    holes keeps them inside its exterior, and the whole list fits one map tile next to the collidable road lines."""
+    from oracle.geometry import point_in_ring
+    from tactics2d_b200.map import load_areas, polygons_to_segments
+
+    per_map = {"inD_1": 6, "inD_2": 14, "inD_3": 11, "inD_4": 19, "rounD_0": 20, "rounD_1": 11, "rounD_2": 15}
+    count = {}
+    for name in list_tiles():
+        areas = load_areas(name)
+        assert len(areas) == per_map.get(name, 0), name
+        for a in areas:
+            assert a.closed and a.type_ == "multipolygon" and len(a.outer) >= 3
+            count[a.subtype] = count.get(a.subtype, 0) + 1
+            x, y = a.outer[:, 0], a.outer[:, 1]
+            assert abs(0.5 * np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y)) > 0.5          # a real region, m^2
+            ring = np.concatenate([a.outer, np.roll(a.outer, -1, 0)], 1)
+            for h in a.inners:
+                assert point_in_ring(h[:, 0], h[:, 1], ring).all()
+        if areas:
+            lines, bounds = load_collidable_segments(name)
+            seg, ps = polygons_to_segments(areas, [])
+            assert len(ps) == len(areas) + 1 and ps[-1] == len(seg)
+            assert len(seg) + len(lines) <= 32767                                            # T2D_MAX_SEGMENTS
+            assert seg[:, [0, 2]].min() >= bounds[0] and seg[:, [0, 2]].max() <= bounds[1]
+            assert seg[:, [1, 3]].min() >= bounds[2] and seg[:, [1, 3]].max() <= bounds[3]
+    assert count == {"freespace": 23, "keepout": 9, "parking": 20, "traffic_island": 17, "vegetation": 20, "walkway": 7}
+    holes = [(a.id_, len(a.inners)) for a in load_areas("inD_2") if a.inners]
+    assert holes == [(30033, 2)]
+    assert [a.subtype for a in load_areas("rounD_0", subtypes=("traffic_island",))] == ["traffic_island"] * len(load_areas("rounD_0", ("traffic_island",)))
+    assert {a.subtype for a in load_areas("inD_4", subtypes=("vegetation", "parking"))} == {"vegetation", "parking"}
+
+
+def test_parked_inside_a_real_area_is_a_static_collision():
+    """StaticCollision on the reference's own map data: a small box (a pedestrian-sized pose) standing in the middle of a
+    vegetation patch or a traffic island of inD_2 / rounD_0 touches none of its edges and still ``intersects`` the Area
+    (collision.py:37-43).  With the areas handed over as objects the oracle reports the containing object (or an earlier one
+    that overlaps it); with the same edges as bare lines it reports nothing - and a box inside one of the walkway's holes
+    is free either way."""
+    from oracle import scenario as O
+    from oracle.geometry import point_in_ring
+    from tactics2d_b200.map import load_areas, polygons_to_segments
+
+    table = dict(half_len=np.array([0.4], np.float32), half_wid=np.array([0.3], np.float32), radius=np.array([0.0], np.float32),
+                 shape=np.array([0], np.int32), model=np.array([0], np.int32))
+    for k in O.TABLE_FLOAT_FIELDS:
+        table.setdefault(k, np.array([1.0], np.float32))
+    rng = np.random.default_rng(11)
+    n_inside = n_hole = 0
+    for name in ("inD_2", "rounD_0"):
+        areas = load_areas(name)
+        seg, ps = polygons_to_segments(areas)
+        a64 = seg.astype(np.float64)
+        for k, a in enumerate(areas):
+            edges = a64[ps[k]:ps[k + 1]]
+            lo, hi = a.outer.min(0), a.outer.max(0)
+            pts = rng.uniform(lo, hi, size=(600, 2))
+            # distance of each point to every edge of this area
+            d = pts[:, None, :] - edges[None, :, :2]
+            e = edges[None, :, 2:] - edges[None, :, :2]
+            t = np.clip((d * e).sum(-1) / np.maximum((e * e).sum(-1), 1e-30), 0, 1)
+            clear = np.sqrt(((d - t[..., None] * e) ** 2).sum(-1)).min(1) > 0.6          # further than the box's circumradius (0.5)
+            inside = point_in_ring(pts[:, 0], pts[:, 1], edges)
+            ring0 = np.concatenate([a.outer, np.roll(a.outer, -1, 0)], 1)
+            in_hole = point_in_ring(pts[:, 0], pts[:, 1], ring0) & ~inside & clear
+            for sel, want_hit in ((inside & clear, True), (in_hole, False)):
+                q = pts[sel][:6]
+                if len(q) == 0:
+                    continue
+                x, y = q[None, :, 0].copy(), q[None, :, 1].copy()
+                h = rng.uniform(-np.pi, np.pi, x.shape)
+                tid = np.zeros(x.shape, np.uint8)
+                fl, _, hs = O.events(x, y, h, tid, table, seg, None, poly_start=ps)
+                plain = O.events(x, y, h, tid, table, seg, None)[2]
+                if want_hit:
+                    assert (fl & 2).all() and (hs >= 0).all() and (hs <= ps[k]).all(), (name, a.id_)
+                    assert np.isin(hs, ps[:-1]).all()                                   # an object's FIRST segment
+                    own = plain < 0                                                     # clear of every edge of every area
+                    assert (hs[own] <= ps[k]).all()
+                    n_inside += int(own.sum())
+                else:
+                    later = [j for j in range(len(areas)) if j != k]
+                    others = np.zeros(x.shape, bool)
+                    for j in later:
+                        others |= point_in_ring(x, y, a64[ps[j]:ps[j + 1]])
+                    free = (plain < 0) & ~others
+                    assert (hs[free] == -1).all(), (name, a.id_)
+                    n_hole += int(free.sum())
+    assert n_inside >= 100 and n_hole >= 4, (n_inside, n_hole)
+
+
 def test_polygons_to_segments_and_pose_recovery():
     """Host helpers of round 2: static objects -> tile format; a get_pose() ring -> (centre, heading, half extents)."""
     from tactics2d_b200.map import polygons_to_segments

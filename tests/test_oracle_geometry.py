@@ -198,3 +198,56 @@ def test_pose_vs_area_polygon_matches_exact_definition():
         n_hit += int(want >= 0)
         n_free += int(want < 0)
     assert n_inside_only >= 5 and n_hit >= 40 and n_free >= 100, (n_inside_only, n_hit, n_free)
+
+
+def test_pose_vs_area_with_holes_matches_exact_definition():
+    """An Area with holes (``Polygon(outer, inners)``, parse_osm.py:461-510; one walkway of inD_2 has two) is one object
+    whose edge range holds all its rings: the edge tests see every ring and the parity of ALL the edges a ray from the centre
+    crosses is "inside the exterior, outside every hole".  Checked against the exact-rational definition - a pose parked
+    wholly inside a hole touches nothing, one in the solid part is a hit, and the object after it keeps its own index."""
+    from oracle import scenario as O
+    from tactics2d_b200.map import Area, polygons_to_segments
+
+    def sq(x0, y0, x1, y1):
+        return [(F(x0), F(y0)), (F(x1), F(y0)), (F(x1), F(y1)), (F(x0), F(y1))]
+
+    objects = [
+        (sq(-30, -20, 10, 20), [sq(-26, -14, -12, 0), [(F(-6), F(4)), (F(6), F(4)), (F(6), F(16)), (F(0), F(10)), (F(-6), F(16))]]),   # two holes, one concave
+        (sq(14, -20, 30, -4), []),
+    ]
+    as_float = lambda ring: np.array([[float(a), float(b)] for a, b in ring])
+    areas = [Area(i, "multipolygon", "walkway", as_float(o), [as_float(h) for h in hs]) for i, (o, hs) in enumerate(objects)]
+    seg, ps = polygons_to_segments(areas)
+    assert ps.tolist() == [0, 4 + 4 + 5, 4 + 4 + 5 + 4]
+    table = dict(half_len=np.array([2.0], np.float32), half_wid=np.array([1.0], np.float32), radius=np.array([0.0], np.float32),
+                 shape=np.array([0], np.int32), model=np.array([0], np.int32))
+    for k in O.TABLE_FLOAT_FIELDS:
+        table.setdefault(k, np.array([1.0], np.float32))
+    rng = np.random.default_rng(5)
+    cases = [(F(-19), F(-7), 0), (F(0), F(8), 1), (F(-20), F(10), 2), (F(22), F(-12), 0), (F(-12), F(-7), 3), (F(40), F(0), 0)]
+    for _ in range(500):
+        cases.append((F(int(rng.integers(-140, 141)), 4), F(int(rng.integers(-100, 101)), 4), int(rng.integers(0, len(TRIPLES)))))
+    n_in_hole = n_solid = n_edge = 0
+    for x, y, t in cases:
+        c, s = TRIPLES[t]
+        pose = corners(x, y, c, s, F(2), F(1))
+        want = -1
+        for p, (outer, holes) in enumerate(objects):
+            rings = [outer] + holes
+            edge = any(seg_seg(pose[i], pose[(i + 1) % 4], r[j], r[(j + 1) % len(r)]) for r in rings for i in range(4) for j in range(len(r)))
+            inside = lambda ring: bool(_winding_inside(ring, (x, y)))               # None (centre on an edge) is an edge hit anyway
+            solid = inside(outer) and not any(inside(h) for h in holes)
+            swallowed = any(in_convex(pose, r[0]) for r in rings)                  # a ring wholly inside the pose
+            if p == 0:
+                n_edge += int(edge)
+                n_solid += int(solid and not edge)
+                n_in_hole += int(not edge and not solid and inside(outer))
+            if edge or solid or swallowed:
+                want = int(ps[p])
+                break
+        heading = float(np.arctan2(float(s), float(c)))
+        fl, hi, hs_ = O.events(np.array([[f(x)]]), np.array([[f(y)]]), np.array([[heading]]), np.zeros((1, 1), np.uint8), table, seg, None, poly_start=ps)
+        assert int(hs_[0, 0]) == want, (x, y, t, int(hs_[0, 0]), want)
+        assert bool(fl[0, 0] & 2) == (want >= 0)
+    assert n_in_hole >= 10 and n_solid >= 40 and n_edge >= 40, (n_in_hole, n_solid, n_edge)
+
