@@ -14,7 +14,10 @@ This module restates the documented GEOS semantics for the shapes the path uses:
 PARITY UNPINNED for this file: no reference test pins a collision result and the
 GEOS build cannot be run here.  ``tests/test_oracle_geometry.py`` cross-checks the
 formulas below against an independent exact-rational definition (edges cross, or
-one shape holds a vertex of the other).
+one shape holds a vertex of the other); ``tests/test_oracle_thirdparty.py`` checks
+them against code that is not ours - sympy.geometry (exact arithmetic, touching and
+tangent cases included) and OpenCV's rotated-rectangle intersection / convex
+clipping (flag and IoU).  Neither is GEOS: the label stays.
 
 Pose: ``Vehicle.get_pose`` (participant/element/vehicle.py:263-281) maps the local
 ring ``[(+L/2,-W/2), (+L/2,+W/2), (-L/2,+W/2), (-L/2,-W/2)]`` (:133-140) by
