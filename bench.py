@@ -429,9 +429,19 @@ def run_ours(args):
     t_wall0 = time.time()
     reps_ms, launches = [], K
     budget_s, t_begin = args.min_seconds, time.time()
-    while len(reps_ms) < args.min_reps or (time.time() - t_begin < budget_s and len(reps_ms) < args.max_reps):
+    while True:
         ms, launches = timed_region()
         reps_ms.append(ms)
+        more = len(reps_ms) < args.min_reps or (time.time() - t_begin < budget_s and len(reps_ms) < args.max_reps)
+        if world_size > 1:
+            # every repetition holds collectives (barrier, max over ranks), so all ranks must run the same number of them:
+            # rank 0's wall clock decides for everybody (each rank reading its own clock can disagree on the last one
+            # and leave a rank waiting in a barrier nobody else enters)
+            flag = torch.tensor([1 if more else 0], dtype=torch.int32, device=device)
+            dist.broadcast(flag, src=0)
+            more = bool(flag.item())
+        if not more:
+            break
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_total = float(np.median(reps_ms))
