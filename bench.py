@@ -294,7 +294,6 @@ def run_ours(args):
         actions.append(torch.from_numpy(synthetic.random_actions(9000 + 1000 * rank + r, (n, m))).to(device))
         pools.append({k: getattr(w, k).clone() for k in ("x", "y", "heading", "speed", "vx", "vy")})
     ones = torch.ones(n, dtype=torch.uint8, device=device)
-    done_all = torch.zeros(world_size * n, dtype=torch.uint8, device=device) if world_size > 1 else None
     # The one exchange of the path: every rank gets every rank's done mask of each step.  Default: our own all-gather
     # kernel over peer memory (t2d_exchange_allgather: put to every rank, signal, wait, copy - one CTA per rank and step);
     # --exchange nccl uses all_gather_into_tensor instead.  Either runs on a side stream under the next tick.
@@ -309,6 +308,10 @@ def run_ours(args):
             args.exchange = "nccl"
             if rank == 0:
                 print(f"[bench] {e}; falling back to --exchange nccl", file=sys.stderr)
+
+    # rows of the gathered mask: the peer kernel pads every rank's row to a multiple of 16 bytes
+    row = peer.pad if peer is not None else n
+    done_all = torch.zeros(world_size * row, dtype=torch.uint8, device=device) if world_size > 1 else None
 
     def restore():
         for w, p in zip(worlds, pools):

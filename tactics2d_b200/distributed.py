@@ -140,6 +140,8 @@ class PeerDoneExchange:
         if done_local.numel() != self.n_local or done_local.dtype != torch.uint8 or not done_local.is_contiguous():
             raise ValueError("done_local must be a contiguous uint8 tensor of this rank's scenarios")
         out = self.out if out is None else out
+        if out.numel() < self.world_size * self.pad or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != done_local.device:
+            raise ValueError(f"out must be a contiguous uint8 tensor of at least world * pad = {self.world_size * self.pad} bytes on the same device")
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self.lib.t2d_exchange_allgather_lagged(self._x, C.c_void_p(done_local.data_ptr()), C.c_void_p(out.data_ptr()),
                                                           self.lag, stream))

@@ -172,6 +172,18 @@ def test_peer_exchange_lag_arguments_are_validated_before_any_device_call():
             PeerDoneExchange(64, "cpu", slots=4, lag=2, lib=_FakeExchangeLib(0))
         ex = PeerDoneExchange(64, "cpu", lag=2, lib=_FakeExchangeLib(0))
         assert ex.slots >= 6 and ex.lag == 2 and ex.calls == 0
+        # the kernel writes world * pad bytes: a shorter / non-uint8 destination or a wrong-sized mask never reaches it
+        import torch
+
+        ex = PeerDoneExchange(100, "cpu", lib=_FakeExchangeLib(0))
+        assert ex.pad == 112
+        for mask, out in ((torch.zeros(100, dtype=torch.uint8), torch.zeros(100, dtype=torch.uint8)),
+                          (torch.zeros(100, dtype=torch.uint8), torch.zeros(112, dtype=torch.int8)),
+                          (torch.zeros(99, dtype=torch.uint8), None),
+                          (torch.zeros(100, dtype=torch.bool), None)):
+            with pytest.raises(ValueError):
+                ex(mask, out)
+        assert ex.calls == 0
     finally:
         if own:
             dist.destroy_process_group()
