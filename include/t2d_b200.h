@@ -338,6 +338,13 @@ int t2d_physics_step(int device, const t2d_type_params* params /*host*/, int int
  * NULL (default) disables it.  Used by profiles/phase_clocks.py. */
 int t2d_debug_set_clock_buffer(t2d_ctx* ctx, long long* device_buffer);
 
+/* Tuning knob of t2d_step, no effect on results: the tick can ask L2 for its first input lines while the previous grid is
+ * still draining (and for the next tile inside its persistent loop).  mode 1: on, 0: off, -1 (default): on unless a
+ * peer-memory done exchange is alive in the process (on one GPU it saves ~1 us per tick at 4096 x 64; next to the
+ * exchange kernel on 8 GPUs it measured slower).  A caller that can time both settings picks with this (bench.py does at
+ * N > 1); the environment variable T2D_PREFETCH sets the initial mode at t2d_create. */
+int t2d_set_prefetch(t2d_ctx* ctx, int mode);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t t2d_launch_count(void);
 

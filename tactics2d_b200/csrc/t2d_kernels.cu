@@ -2434,6 +2434,13 @@ int t2d_step_host(t2d_ctx* c, const float* action_host, uint8_t* flags, int16_t*
   return T2D_OK;
 }
 
+int t2d_set_prefetch(t2d_ctx* c, int mode) {
+  if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
+  if (mode < -1 || mode > 1) return fail(T2D_E_INVALID, "prefetch mode must be -1 (policy), 0 (off) or 1 (on)");
+  c->prefetch_override = mode;
+  return T2D_OK;
+}
+
 int t2d_set_ego_action(t2d_ctx* c, const float* ego_action) {
   if (!c) return fail(T2D_E_INVALID, "ctx is NULL");
   if (ego_action && reinterpret_cast<uintptr_t>(ego_action) % 8 != 0) return fail(T2D_E_INVALID, "ego_action must be 8-byte aligned");

@@ -376,6 +376,11 @@ class BatchedWorld:
         self.frame += self.interval
         return hb[0], hb[1]
 
+    def set_prefetch(self, mode: int):
+        """Tuning knob of the tick (``t2d_set_prefetch``), no effect on results: 1 / 0 = ask L2 for the next inputs early or
+        not, -1 = the library's policy (on unless a peer-memory done exchange is alive)."""
+        _lib.check(self.lib.t2d_set_prefetch(self._ctx, int(mode)))
+
     def env_epilogue(self, reset_trackers_on_done: bool = True) -> "EnvResult":
         """Reward, terminated, truncated, done and the per-participant TrafficStatus of the last tick in ONE launch
         (``t2d_env_epilogue``: ParkingEnv.step after check_status, envs/parking.py:240-256 and _get_reward :148-190)."""
